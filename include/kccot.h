@@ -1,0 +1,138 @@
+/*
+ * kccot.h — C ABI of libkccot.so: the B200 (sm_100a) causal-OT loss path of KCCOT-GAN.
+ *
+ * The reference (neuripss2020/kccotgan) has no FFI: its loss path is a set of plain Python
+ * functions over TensorFlow eager tensors (gan_utils.py, data_utils.py:478-586).  This header is
+ * the boundary a maintainer binds instead: every entry point below replaces the arithmetic of the
+ * reference function cited next to it.  The Python mirror of the reference interface
+ * (kccotgan_b200/gan_utils.py, data_utils.py) calls these through ctypes; INTEGRATION.md shows
+ * the stub for the reference's own TensorFlow training loop.
+ *
+ * Conventions
+ *   - All pointers are DEVICE pointers to contiguous fp32 unless stated; the caller owns every
+ *     buffer (inputs, outputs, saved state, workspace).  The library allocates nothing per call
+ *     and keeps no pointer after return.
+ *   - `stream` is a cudaStream_t passed as void*.  Calls only enqueue work; none synchronises.
+ *   - Return 0 on success, a negative KCCOT_E* code otherwise; kccot_last_error() gives the text
+ *     (thread-local).  There is no CPU fallback: without a CUDA device every compute call fails.
+ *   - Videos are [B, ...] tensors flattened to rows of length K (any order of the trailing axes:
+ *     the cost sums over all of them, gan_utils.py:14-17,216-220).  h / M are [B, T, J].
+ *   - "nprob" batches independent problems along a leading axis of every tensor.
+ */
+#ifndef KCCOT_H_
+#define KCCOT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KCCOT_VERSION 100
+
+/* error codes */
+#define KCCOT_OK 0
+#define KCCOT_EINVAL (-1)   /* bad shape / null pointer / misaligned buffer  -> Python ValueError */
+#define KCCOT_ECUDA (-2)    /* CUDA runtime / driver error                   -> Python RuntimeError */
+#define KCCOT_EWORKSPACE (-3)
+#define KCCOT_EUNSUPPORTED (-4)
+
+/* kernel-path selection flags (shape-based AUTO is what the product uses; the explicit values
+ * exist so that tests can check the tensor-core path against the CUDA-core path) */
+#define KCCOT_PATH_AUTO 0
+#define KCCOT_PATH_SIMT 1      /* fp32 CUDA-core kernels, direct (x-y)^2 form, any shape */
+#define KCCOT_PATH_TCGEN05 2   /* TMA + tcgen05 3xTF32 kernels (needs K % 4 == 0, 16-B aligned rows) */
+#define KCCOT_FLAG_ACCUMULATE 16  /* gradient outputs: add into the buffer instead of overwriting */
+
+int kccot_version(void);
+const char* kccot_last_error(void);
+/* 0 if the current device is sm_100 (B200); KCCOT_EUNSUPPORTED otherwise. */
+int kccot_device_check(void);
+/* number of kernels this library has launched so far in this process (bench.py's gpu_launches) */
+unsigned long long kccot_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Cost matrices — gan_utils.py:6-18 (cost_xy), :21-43 (modified_cost), :46-72 (bi_causal_...)
+ *   C[p,i,j] = s * sum_k (x[p,i,k] - y[p,j,k])^2
+ *            + s * sum_{t<T-1,c} h1[p,i,t,c] * (M1[p,j,t+1,c] - M1[p,j,t,c])      (if h1 != NULL)
+ *            + s * sum_{t<T-1,c} h2[p,i,t,c] * (M2[p,j,t+1,c] - M2[p,j,t,c])      (if h2 != NULL)
+ * x [nprob,Bx,K], y [nprob,By,K], h* [nprob,Bx,T,J], M* [nprob,By,T,J], C [nprob,Bx,By].
+ * x == y (same pointer) marks a self-cost: the diagonal is exactly 0 as in the reference.
+ * ------------------------------------------------------------------------------------------ */
+size_t kccot_cost_workspace_bytes(int nprob, int Bx, int By, long long K);
+int kccot_cost_fwd(const float* x, const float* y, int nprob, int Bx, int By, long long K,
+                   const float* h1, const float* M1, const float* h2, const float* M2, int T, int J,
+                   float s, float* C, void* ws, size_t ws_bytes, int flags, void* stream);
+
+/* The three cost matrices of the mixed loss in one pass over the videos —
+ * gan_utils.py:221-223: xy = (real,fake,h_fake,m_real), xx = (real,real,h_real,m_real),
+ * yy = (fake,fake,h_fake,m_fake).  C3 [nprob,3,B,B] in the order xy, xx, yy. */
+size_t kccot_mixed_cost_workspace_bytes(int nprob, int B, long long K);
+int kccot_mixed_cost_fwd(const float* real, const float* fake, int nprob, int B, long long K,
+                         const float* h_fake, const float* m_real, const float* h_real,
+                         const float* m_fake, int T, int J, float s, float* C3, void* ws,
+                         size_t ws_bytes, int flags, void* stream);
+
+/* Adjoint of the squared-distance part: gx[p,i,:] = 2s * sum_j Cbar[p,i,j] (x_i - y_j),
+ * gy[p,j,:] = 2s * sum_i Cbar[p,i,j] (y_j - x_i).  gx / gy may be NULL (not needed). */
+size_t kccot_cost_bwd_workspace_bytes(int nprob, int Bx, int By, long long K);
+int kccot_cost_bwd(const float* Cbar, const float* x, const float* y, int nprob, int Bx, int By,
+                   long long K, float s, float* gx, float* gy, void* ws, size_t ws_bytes, int flags,
+                   void* stream);
+/* Adjoint of one martingale term: gh[:, :-1] = s*Cbar@DeltaM, gh[:, -1] = 0; gM from s*Cbar^T@h. */
+int kccot_martingale_bwd(const float* Cbar, const float* h, const float* M, int nprob, int Bx, int By,
+                         int T, int J, float s, float* gh, float* gM, int flags, void* stream);
+/* Adjoint of kccot_mixed_cost_fwd.  Cbar3 [nprob,3,B,B] already carries the 2,-1,-1 weights and
+ * the upstream gradient.  g_real may be NULL (data needs no gradient, kernel_train.py:289). */
+size_t kccot_mixed_cost_bwd_workspace_bytes(int nprob, int B, long long K);
+int kccot_mixed_cost_bwd(const float* Cbar3, const float* real, const float* fake, int nprob, int B,
+                         long long K, const float* h_fake, const float* m_real, const float* h_real,
+                         const float* m_fake, int T, int J, float s, float* g_real, float* g_fake,
+                         float* gh_fake, float* gm_real, float* gh_real, float* gm_fake, void* ws,
+                         size_t ws_bytes, int flags, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Log-domain Sinkhorn — gan_utils.py:138-165 (compute_sinkhorn), :86-121 (benchmark_sinkhorn)
+ * nsolve independent B x B problems.  L iterations of the u / v updates with uniform marginals;
+ * after iteration n (1-based) the solve stops if thresh > sum|u - u_prev| and
+ * (exit_on_index ? n-1 >= Lmin : n >= Lmin)   [:159 vs :116].  The test runs on the device.
+ * Saved for the backward (internal units: potentials * log2(e)/eps, cost shifted by its minimum):
+ *   u_hist, v_hist [nsolve, L+1, B];  nits [nsolve] int32;  cost [nsolve] = sum(pi * C).
+ * ------------------------------------------------------------------------------------------ */
+size_t kccot_sinkhorn_workspace_bytes(int nsolve, int B, int L);
+int kccot_sinkhorn_fwd(const float* C, int nsolve, int B, float eps, int L, int Lmin, float thresh,
+                       int exit_on_index, float* u_hist, float* v_hist, int32_t* nits, float* cost,
+                       void* ws, size_t ws_bytes, void* stream);
+/* Reverse mode through the executed iterations (the reference has no stop_gradient; TF's tape
+ * unrolls the loop).  Cbar[n] = gcost[n] * d cost[n] / d C[n].  gcost [nsolve] on the device. */
+int kccot_sinkhorn_bwd(const float* C, int nsolve, int B, float eps, int L, const float* u_hist,
+                       const float* v_hist, const int32_t* nits, const float* gcost, float* Cbar,
+                       void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Martingale penalty p_M — gan_utils.py:179-201.  M [B,T,J]; pm [1]; gM [B,T,J] = gpm * dpm/dM.
+ * ------------------------------------------------------------------------------------------ */
+int kccot_pm_fwd(const float* M, int B, int T, int J, float reg_lam, float s, float* pm,
+                 float* stats /* [2*J + (T-1)*J] saved: mean_j, std_j, A_tj */, void* stream);
+int kccot_pm_bwd(const float* M, int B, int T, int J, float reg_lam, float s, const float* stats,
+                 const float* gpm /* device scalar */, float* gM, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Gaussian kernel smoothing — data_utils.py:503-521 (temporal_convolution, mode 1) and
+ * :552-582 (gaussian_convolution3D, mode 3).  x, out [B,H,T,W,C].  filt_* are the dense
+ * [n,n] REFLECT-pad + 7-tap filter matrices built by the host (row p = output position).
+ * out = conv(x) / max(conv(x)); maxval [1] is saved for the backward.
+ * ------------------------------------------------------------------------------------------ */
+size_t kccot_smooth_workspace_bytes(int mode, int B, int H, int T, int W, int C);
+int kccot_smooth_fwd(int mode, const float* x, int B, int H, int T, int W, int C, const float* filt_h,
+                     const float* filt_t, const float* filt_w, float* out, float* maxval, void* ws,
+                     size_t ws_bytes, void* stream);
+int kccot_smooth_bwd(int mode, const float* gout, const float* out, const float* maxval, int B, int H,
+                     int T, int W, int C, const float* filt_h, const float* filt_t,
+                     const float* filt_w, float* gx, void* ws, size_t ws_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KCCOT_H_ */

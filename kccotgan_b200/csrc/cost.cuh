@@ -1,0 +1,49 @@
+// Internal interfaces of the cost path (shared by cost_simt.cu, gram_tcgen05.cu, cost_abi.cu).
+#pragma once
+#include "common.cuh"
+
+namespace kccot {
+
+// One cost matrix to finalise: C[p,i,j] = s * sum_ks part[...] + s * martingale terms.
+struct CostBlock {
+  const float* part;       // partial squared distances
+  long long prob_stride;   // elements between problems in `part`
+  long long ks_stride;     // elements between k-slabs
+  int ld, row_off, col_off, nks;
+  const float *h1, *M1, *h2, *M2;   // martingale pairs (row-indexed h, column-indexed M); may be null
+  float* C;
+  long long C_prob_stride;
+  int Bx, By, zero_diag;
+};
+struct CostBlocks {
+  CostBlock b[3];
+};
+
+// cost_simt.cu
+void choose_ksplit_simt(int nprob, int Bx, int By, long long K, int* ksplit, long long* kslab);
+int launch_sqdist_partials_simt(const float* x, const float* y, int nprob, int Bx, int By, long long K,
+                                int ksplit, long long kslab, float* part, cudaStream_t st);
+int launch_cost_finalize(const CostBlocks& blocks, int nblocks, int nprob, int T, int J, float s,
+                         cudaStream_t st);
+int launch_cost_bwd_simt(const float* W, long long sr, long long sc, long long wprob, const float* a,
+                         const float* b, int nprob, int Ba, int Bb, long long K, float s, float* g,
+                         int accumulate, cudaStream_t st);
+int launch_martingale_bwd(const float* Cbar, long long cprob, const float* h, const float* M, int nprob,
+                          int Bx, int By, int T, int J, float s, float w, float* gh, float* gM,
+                          int acc_h, int acc_M, cudaStream_t st);
+
+// gram_tcgen05.cu — stacked-row tensor-core path.  Z = [x; y] (or x alone when y == nullptr),
+// R = rows of Z <= 128.  Writes partial squared-distance tiles part[p][ks][128][128].
+bool tc_sqdist_supported(const float* x, const float* y, int Bx, int By, long long K);
+void tc_sqdist_plan(int nprob, int R, long long K, int* ksplit, int* kblocks_per_slab);
+int launch_sqdist_partials_tc(const float* x, const float* y, int nprob, int Bx, int By, long long K,
+                              int ksplit, int kblocks_per_slab, float* part, cudaStream_t st);
+
+// grad_tcgen05.cu — out[p,r,:] (+)= 2s * sum_c W[p,r,c] * (z[p,r,:] - z[p,c,:]) over the stacked
+// rows z = [x; y]; W [nprob,128,128] (zero padded).  gx / gy may be null.
+bool tc_grad_supported(const float* x, const float* y, int Bx, int By, long long K, const float* gx,
+                       const float* gy);
+int launch_grad_tc(const float* W, const float* x, const float* y, int nprob, int Bx, int By, long long K,
+                   float s, float* gx, float* gy, int accumulate, cudaStream_t st);
+
+}  // namespace kccot

@@ -1,0 +1,106 @@
+"""The C-ABI library builds, loads, and exports every symbol include/kccot.h declares; host-side
+argument validation.  CPU only (no compute calls)."""
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from kccotgan_b200 import build, _lib
+    build.build()
+    return _lib.load()
+
+
+def test_header_symbols_exported(lib):
+    from kccotgan_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "kccot.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(kccot_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in kccot.h but not exported"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+
+
+def test_version_and_no_cpu_fallback(lib):
+    from kccotgan_b200 import _lib
+    assert lib.kccot_version() == 100
+    if not torch.cuda.is_available():
+        assert lib.kccot_device_check() != 0
+        assert "no CUDA device" in _lib.last_error()
+
+
+def test_workspace_queries(lib):
+    assert lib.kccot_mixed_cost_workspace_bytes(1, 64, 122880) > 0
+    assert lib.kccot_cost_workspace_bytes(1, 64, 64, 1000) > 0
+    assert lib.kccot_sinkhorn_workspace_bytes(3, 64, 100) >= 256
+    assert lib.kccot_sinkhorn_workspace_bytes(1, 512, 100) > 512 * 4 * 4
+    assert lib.kccot_smooth_workspace_bytes(3, 2, 8, 8, 8, 1) >= 2 * 2 * 8 * 8 * 8 * 4
+    assert lib.kccot_cost_workspace_bytes(0, 64, 64, 1000) == 0
+
+
+def test_argument_errors_are_value_errors(lib):
+    from kccotgan_b200 import _lib
+    with pytest.raises(ValueError):
+        _lib.call("kccot_cost_fwd", None, None, 1, 8, 8, 64, None, None, None, None, 0, 0, 0.1, None, None, 0, 0, None)
+    with pytest.raises(ValueError):
+        _lib.call("kccot_smooth_fwd", 2, None, 1, 8, 8, 8, 1, None, None, None, None, None, None, 0, None)
+    assert "2d" in _lib.last_error()
+
+
+def test_python_surface_matches_reference_signatures():
+    """Same names / positional orders / defaults as gan_utils.py and KernelSmoothing."""
+    import inspect
+    from kccotgan_b200 import gan_utils as g
+    from kccotgan_b200.data_utils import KernelSmoothing
+    sig = lambda f: str(inspect.signature(f))  # noqa: E731
+    assert sig(g.cost_xy) == "(x, y, scaling_coef)"
+    assert sig(g.modified_cost) == "(x, y, h, M, scaling_coef)"
+    assert sig(g.bi_causal_modified_cost) == "(x, y, hy, Mx, hx, My, scaling_coef)"
+    assert sig(g.benchmark_sinkhorn) == "(x, y, scaling_coef, epsilon=1.0, L=10, Lmin=10)"
+    assert sig(g.compute_sinkhorn) == "(x, y, hy, Mx, scaling_coef, hx=None, My=None, epsilon=1.0, L=100, bi_causal=False)"
+    assert sig(g.compute_N) == "(M)"
+    assert sig(g.scale_invariante_martingale_regularization) == "(M, reg_lam, scaling_coef)"
+    assert sig(g.compute_sinkhorn_loss) == ("(f_real, f_fake, scaling_coef, sinkhorn_eps, sinkhorn_l, h_fake, m_real, "
+                                            "h_real, m_fake, video=True)")
+    assert sig(KernelSmoothing.__init__) == "(self, temporal_kernel_size=6, spatial_kernel_size=8)"
+    assert sig(KernelSmoothing.annealing_sigma) == "(self, init_sigma, step, decay_steps=500, decay_rate=0.975)"
+    ks = KernelSmoothing(6, 6)
+    assert ks.temporal_radius == 3 and ks.spatial_radius == 3
+    assert ks.annealing_sigma(5.0, 1000) == 5.0 * 0.975 ** 2
+
+
+def test_cpu_tensors_rejected():
+    from kccotgan_b200 import gan_utils as g
+    x = torch.rand(4, 3, 8)
+    with pytest.raises(ValueError, match="CUDA"):
+        g.cost_xy(x, x, 0.1)
+    with pytest.raises(ValueError):
+        g.compute_sinkhorn_loss(x, x, 0.1, 1.0, 100, x, x, x, x, video=False)
+
+
+def test_product_does_not_import_oracle():
+    """The oracle is test infrastructure: nothing under kccotgan_b200/ may reference it."""
+    pkg = os.path.join(ROOT, "kccotgan_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert "oracle" not in src.replace("# oracle", ""), fn
+
+
+def test_filter_matrix_matches_oracle():
+    import numpy as np
+    from kccotgan_b200.data_utils import KernelSmoothing
+    from oracle import closed_form as cf
+    ks = KernelSmoothing(6, 6)
+    for n in (4, 7, 12, 64):
+        A = ks._filter_matrix(n, 3, 5.0, "cpu").numpy()
+        assert np.allclose(A, cf._filter_matrix(n, 3, 5.0), atol=1e-7)
+        assert np.allclose(A.sum(axis=1), 1.0, atol=1e-6)
+    with pytest.raises(ValueError):
+        ks._filter_matrix(3, 3, 5.0, "cpu")

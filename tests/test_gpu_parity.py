@@ -1,0 +1,276 @@
+"""T2: the CUDA path (through the C ABI / ctypes) against the golden vectors of the reference's own
+source and against the fp64 oracle on the same inputs.  Needs a B200: `pytest -m gpu`.
+
+Tolerances (BASELINE.json north_star: "within 1e-4 relative, in fp32"):
+  * each loss term: |term - ref| <= 1e-4 * max(|xy|,|xx|,|yy|)   (the mixed loss 2xy-xx-yy cancels,
+    so it is normalised by the largest term);
+  * each gradient: rel-L2 <= 1e-4 against the fp64 reference run;
+  * cost matrices: max abs error <= 1e-6 * max|C| (what the reference's own fp32 run achieves).
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, rel_l2
+from kccotgan_b200.synthetic import CONFIGS, GRAD_NAMES, INPUT_ORDER, make_inputs
+
+pytestmark = pytest.mark.gpu
+
+LOSS_TOL = 1e-4
+GRAD_TOL = 1e-4
+COST_TOL = 1e-6
+
+
+@pytest.fixture(scope="module")
+def gu():
+    from kccotgan_b200 import _lib, gan_utils
+    assert _lib.load().kccot_device_check() == 0, _lib.last_error()
+    return gan_utils
+
+
+@pytest.fixture(autouse=True)
+def _reset_path():
+    from kccotgan_b200 import functional
+    functional.set_path("auto")
+    yield
+    functional.set_path("auto")
+
+
+def dev(a, grad=False):
+    t = torch.as_tensor(np.asarray(a), dtype=torch.float32).cuda()
+    return t.requires_grad_(True) if grad else t
+
+
+def maxrel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / np.abs(b).max())
+
+
+# ---------------------------------------------------------------------------------------------
+# small golden: every gan_utils function
+# ---------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def small():
+    return load_golden("gan_utils_small.npz")
+
+
+def test_cost_functions_small(gu, small):
+    g = small
+    s = float(g["scaling_coef"])
+    x, y, hy, Mx, hx, My = (dev(g[k]) for k in ("x", "y", "hy", "Mx", "hx", "My"))
+    assert maxrel(gu.cost_xy(x, y, s).cpu(), g["cost_xy"]) < COST_TOL
+    assert maxrel(gu.modified_cost(x, y, hy, Mx, s).cpu(), g["modified_cost"]) < COST_TOL
+    assert maxrel(gu.bi_causal_modified_cost(x, y, hy, Mx, hx, My, s).cpu(), g["bi_causal_modified_cost"]) < COST_TOL
+    assert np.allclose(gu.compute_N(Mx[:, :, 0]).cpu().numpy(), g["compute_N"], atol=1e-6)
+    cxx = gu.cost_xy(x, x, s).cpu().numpy()
+    assert np.all(np.diag(cxx) == 0.0)          # exact zeros as in the reference
+
+
+@pytest.mark.parametrize("tag,kw", [("default", {}), ("eps0p8", dict(epsilon=0.8)),
+                                    ("eps0p3_L20", dict(epsilon=0.3, L=20)), ("L130", dict(L=130)),
+                                    ("eps5_L400", dict(epsilon=5.0, L=400))])
+def test_compute_sinkhorn_small(gu, small, tag, kw):
+    g = small
+    s = float(g["scaling_coef"])
+    lv = [dev(g[k], grad=True) for k in ("x", "y", "hy", "Mx")]
+    c = gu.compute_sinkhorn(lv[0], lv[1], lv[2], lv[3], s, **kw)
+    ref = float(g[f"compute_sinkhorn_{tag}"])
+    assert abs(float(c) - ref) <= LOSS_TOL * abs(ref)
+    grads = torch.autograd.grad(c, lv)
+    for n, a in zip(("x", "y", "hy", "Mx"), grads):
+        assert rel_l2(a.cpu().numpy(), g[f"compute_sinkhorn_{tag}_grad_{n}"]) < GRAD_TOL, (tag, n)
+
+
+def test_bicausal_small(gu, small):
+    g = small
+    s = float(g["scaling_coef"])
+    lv = [dev(g[k], grad=True) for k in ("x", "y", "hy", "Mx", "hx", "My")]
+    c = gu.compute_sinkhorn(lv[0], lv[1], lv[2], lv[3], s, lv[4], lv[5], epsilon=0.5, L=50, bi_causal=True)
+    ref = float(g["compute_sinkhorn_bicausal"])
+    assert abs(float(c) - ref) <= LOSS_TOL * abs(ref)
+    for n, a in zip(("x", "y", "hy", "Mx", "hx", "My"), torch.autograd.grad(c, lv)):
+        assert rel_l2(a.cpu().numpy(), g[f"compute_sinkhorn_bicausal_grad_{n}"]) < GRAD_TOL, n
+
+
+@pytest.mark.parametrize("tag,kw", [("default", {}), ("eps0p5_L40_Lmin5", dict(epsilon=0.5, L=40, Lmin=5)),
+                                    ("eps2_L200_Lmin10", dict(epsilon=2.0, L=200, Lmin=10))])
+def test_benchmark_sinkhorn_small(gu, small, tag, kw):
+    g = small
+    s = float(g["scaling_coef"])
+    lv = [dev(g[k], grad=True) for k in ("x", "y")]
+    c = gu.benchmark_sinkhorn(lv[0], lv[1], s, **kw)
+    ref = float(g[f"benchmark_sinkhorn_{tag}"])
+    assert abs(float(c) - ref) <= LOSS_TOL * abs(ref)
+    gx, gy = torch.autograd.grad(c, lv)
+    assert rel_l2(gx.cpu().numpy(), g[f"benchmark_sinkhorn_{tag}_grad_x"]) < GRAD_TOL
+    assert rel_l2(gy.cpu().numpy(), g[f"benchmark_sinkhorn_{tag}_grad_y"]) < GRAD_TOL
+
+
+def test_eps_l_arguments_ignored(gu, small):
+    g = small
+    s = float(g["scaling_coef"])
+    args = [dev(g[k]) for k in ("x", "y")], [dev(g[k]) for k in ("hy", "Mx", "hx", "My")]
+    a = gu.compute_sinkhorn_loss(args[0][0], args[0][1], s, 0.8, 100, *args[1], video=False)
+    b = gu.compute_sinkhorn_loss(args[0][0], args[0][1], s, 5.0, 7, *args[1], video=False)
+    assert float(a) == float(b)
+    assert abs(float(a) - float(g["loss_novideo"])) <= LOSS_TOL * 2.0
+
+
+def test_pm_small(gu, small):
+    g = small
+    for tag, key in (("a", "Mx"), ("b", "My")):
+        M = dev(g[key], grad=True)
+        pm = gu.scale_invariante_martingale_regularization(M, 1.3, float(g["scaling_coef"]))
+        ref = float(g[f"pm_{tag}"])
+        assert abs(float(pm) - ref) <= LOSS_TOL * abs(ref)
+        gm, = torch.autograd.grad(pm, M)
+        assert rel_l2(gm.cpu().numpy(), g[f"pm_{tag}_grad"]) < GRAD_TOL
+
+
+# ---------------------------------------------------------------------------------------------
+# mixed loss at the BASELINE configs
+# ---------------------------------------------------------------------------------------------
+def _run_loss(gu, inp, s):
+    leaves = [inp[k].clone().cuda().requires_grad_(True) for k in INPUT_ORDER]
+    r, f, hf, mr, hr, mf = leaves
+    from kccotgan_b200.gan_utils import sinkhorn_loss_terms
+    loss, terms = sinkhorn_loss_terms(r, f, s, hf, mr, hr, mf)
+    loss2 = gu.compute_sinkhorn_loss(r, f, s, 0.8, 100, hf, mr, hr, mf, video=True)
+    grads = torch.autograd.grad(loss2, leaves)
+    assert float(loss) == float(loss2)
+    return float(loss2), terms.cpu().numpy().astype(np.float64), [a.cpu().numpy() for a in grads]
+
+
+@pytest.mark.parametrize("path", ["simt", "tcgen05"])
+@pytest.mark.parametrize("kind", ["uniform", "video"])
+@pytest.mark.parametrize("cfg", ["cfg1", "cfg2", "cfg3"])
+def test_mixed_loss_reduced(gu, cfg, kind, path):
+    from kccotgan_b200 import functional
+    functional.set_path(path)
+    g = load_golden(f"loss_{cfg}_reduced_{kind}.npz")
+    s = float(g["scaling_coef"])
+    inp = {k: torch.from_numpy(g[k]) for k in INPUT_ORDER}
+    loss, terms, grads = _run_loss(gu, inp, s)
+    ref_terms = np.array([float(g["loss_xy"]), float(g["loss_xx"]), float(g["loss_yy"])])
+    scale = np.abs(ref_terms).max()
+    assert np.abs(terms - ref_terms).max() <= LOSS_TOL * scale, (terms, ref_terms)
+    assert abs(loss - float(g["loss"])) <= LOSS_TOL * scale
+    errs = {n: rel_l2(a, g["grad_" + n]) for n, a in zip(GRAD_NAMES, grads)}
+    print(cfg, kind, path, "loss err", abs(loss - float(g["loss"])) / scale, errs)
+    for n, e in errs.items():
+        assert e < GRAD_TOL, (n, e)
+
+
+@pytest.mark.parametrize("path", ["simt", "tcgen05"])
+@pytest.mark.parametrize("name,kind", [("cfg1_mmnist", "uniform"), ("cfg1_mmnist", "video"), ("cfg2_mazes", "uniform")])
+def test_mixed_loss_full_size(gu, name, kind, path):
+    from kccotgan_b200 import functional
+    functional.set_path(path)
+    g = load_golden(f"loss_{name}_full_{kind}.npz")
+    s = float(g["scaling_coef"])
+    c = {k: v for k, v in CONFIGS[name].items() if k != "nprob"}
+    inp = make_inputs(J=8, kind=kind, seed=1, **c)
+    # cost matrices first (the numerically delicate part: |C| ~ 1e3, eps = 1)
+    from kccotgan_b200.functional import CostFn
+    r, f = inp["real"].cuda(), inp["fake"].cuda()
+    Cxy = CostFn.apply(r, f, inp["h_fake"].cuda(), inp["m_real"].cuda(), None, None, s).cpu().numpy()
+    print(name, kind, path, "C_xy max abs err", np.abs(Cxy - g["C_xy"]).max(), "max |C|", np.abs(g["C_xy"]).max())
+    assert maxrel(Cxy, g["C_xy"]) < COST_TOL
+    loss, terms, grads = _run_loss(gu, inp, s)
+    ref_terms = np.array([float(g["loss_xy"]), float(g["loss_xx"]), float(g["loss_yy"])])
+    scale = np.abs(ref_terms).max()
+    print("terms", terms, ref_terms, "loss", loss, float(g["loss"]))
+    assert np.abs(terms - ref_terms).max() <= LOSS_TOL * scale
+    assert abs(loss - float(g["loss"])) <= LOSS_TOL * scale
+    for n, a in zip(GRAD_NAMES, grads):
+        if ("grad_" + n) in g:
+            e = rel_l2(a, g["grad_" + n])
+        else:
+            st = int(g["grad_" + n + "_stride"])
+            flat = a.reshape(-1).astype(np.float64)
+            e = rel_l2(flat[::st], g["grad_" + n + "_sample"])
+            assert abs(np.linalg.norm(flat) - float(g["grad_" + n + "_norm"])) <= 1e-4 * float(g["grad_" + n + "_norm"])
+            probe = np.random.default_rng(7).standard_normal(flat.size)
+            assert abs(flat @ probe - float(g["grad_" + n + "_proj"])) <= 2e-4 * float(g["grad_" + n + "_norm"]) * np.sqrt(flat.size) / 30
+        print("  grad", n, e)
+        assert e < GRAD_TOL, (n, e)
+
+
+# ---------------------------------------------------------------------------------------------
+# Sinkhorn kernels in isolation against the fp64 oracle on the same (fp32-rounded) cost
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,eps,L", [(64, 1.0, 100), (32, 0.8, 100), (17, 0.3, 40), (64, 1.0, 250), (96, 1.0, 60),
+                                     (200, 0.7, 30), (96, 2.0, 300)])
+def test_sinkhorn_kernels_vs_oracle(B, eps, L):
+    from kccotgan_b200.functional import SinkhornFn
+    from oracle import closed_form as cf
+    rng = np.random.default_rng(B + L)
+    C = (900.0 + 4.0 * rng.standard_normal((2, B, B))).astype(np.float32)
+    C[1] = np.abs(C[1] - 900.0) * 3.0                     # a small-valued problem next to a large-valued one
+    Ct = torch.from_numpy(C).cuda().requires_grad_(True)
+    cost, nits = SinkhornFn.apply(Ct, eps, L, 100, 1e-2, False)
+    w = torch.tensor([1.0, -2.0], device="cuda")
+    gC, = torch.autograd.grad((cost * w).sum(), Ct)
+    for n in range(2):
+        ref, uh, vh, rn = cf.sinkhorn_forward(C[n].astype(np.float64), eps, L, Lmin=100, thresh=1e-2)
+        assert int(nits[n]) == rn, (int(nits[n]), rn)
+        assert abs(float(cost[n]) - ref) <= LOSS_TOL * abs(ref), (float(cost[n]), ref)
+        Cb = cf.sinkhorn_backward(C[n].astype(np.float64), eps, uh, vh, rn, gbar=float(w[n]))
+        e = rel_l2(gC[n].cpu().numpy(), Cb)
+        print(B, eps, L, n, "nits", rn, "cost rel", abs(float(cost[n]) - ref) / abs(ref), "Cbar rel-L2", e)
+        assert e < GRAD_TOL
+
+
+# ---------------------------------------------------------------------------------------------
+# smoothing
+# ---------------------------------------------------------------------------------------------
+def test_smoothing_golden():
+    from kccotgan_b200.data_utils import KernelSmoothing
+    g = load_golden("smoothing.npz")
+    ks = KernelSmoothing(temporal_kernel_size=6, spatial_kernel_size=6)
+    for sig in (5.0, 1.7):
+        assert rel_l2(ks.gaussian_kernel1d(3, sig).cpu().numpy(), g[f"kernel1d_sigma{sig}"]) < 1e-6
+        assert rel_l2(ks.gaussian_kernel3d(3, sig).cpu().numpy(), g[f"kernel3d_sigma{sig}"]) < 1e-6
+    assert ks.annealing_sigma(5.0, 1000) == float(g["annealing_sigma_5_1000"])
+    with pytest.raises(ValueError):
+        ks.spatial_convolution(torch.rand(2, 8, 5, 8, 3, device="cuda"), 5.0)
+    for tag in ("nc3", "nc1", "tie"):
+        for mode, fn in (("1d", ks.temporal_convolution), ("3d", ks.gaussian_convolution3D)):
+            for sig in (5.0, 1.7):
+                x = dev(g[f"x_{tag}"], grad=True)
+                out = fn(x, sig)
+                gx, = torch.autograd.grad(out, x, dev(g[f"gout_{tag}"]))
+                eo = rel_l2(out.detach().cpu().numpy(), g[f"{mode}_{tag}_sigma{sig}"])
+                eg = rel_l2(gx.cpu().numpy(), g[f"{mode}_{tag}_sigma{sig}_grad"])
+                assert float(out.max()) == 1.0
+                assert eo < 1e-5 and eg < GRAD_TOL, (tag, mode, sig, eo, eg)
+
+
+def test_smoothing_full_frame():
+    """64x64x3 frames (cfg 3 shape at reduced batch) against the fp64 oracle."""
+    from kccotgan_b200.data_utils import KernelSmoothing
+    from oracle import closed_form as cf
+    ks = KernelSmoothing(6, 6)
+    torch.manual_seed(3)
+    x = torch.rand(3, 64, 12, 64, 3)
+    go = torch.randn(3, 64, 12, 64, 3)
+    for mode, fn, cfn in (("1d", ks.temporal_convolution, cf.temporal_convolution),
+                          ("3d", ks.gaussian_convolution3D, cf.gaussian_convolution3D)):
+        xl = x.cuda().requires_grad_(True)
+        out = fn(xl, 5.0)
+        gx, = torch.autograd.grad(out, xl, go.cuda())
+        ro, rg = cfn(x.numpy(), 5.0, grad_out=go.numpy())
+        assert rel_l2(out.detach().cpu().numpy(), ro) < 1e-5, mode
+        assert rel_l2(gx.cpu().numpy(), rg) < GRAD_TOL, mode
+
+
+def test_errors_raise(gu):
+    x = torch.rand(8, 4, 16, device="cuda")
+    with pytest.raises(ValueError):
+        gu.cost_xy(x.cpu(), x, 0.1)
+    with pytest.raises(ValueError):
+        gu.cost_xy(x.double(), x.double(), 0.1)
+    with pytest.raises(ValueError):
+        gu.cost_xy(x, torch.rand(8, 4, 12, device="cuda"), 0.1)
+    with pytest.raises(ValueError):
+        gu.compute_sinkhorn_loss(x, x, 0.1, 1.0, 100, x, x, x, x, video=True)
