@@ -74,6 +74,12 @@ int kccot_mixed_cost_fwd(const float* real, const float* fake, int nprob, int B,
                          const float* m_fake, int T, int J, float s, float* C3, void* ws,
                          size_t ws_bytes, int flags, void* stream);
 
+/* First half of kccot_mixed_cost_fwd on its own: only the split-K partial squared distances of the
+ * stacked rows [real; fake] are written to the workspace (the HBM-bound pass over the videos).
+ * Exposed so that the streaming kernel can be timed and profiled in isolation. */
+int kccot_mixed_sqdist_partials(const float* real, const float* fake, int nprob, int B, long long K,
+                                void* ws, size_t ws_bytes, int flags, void* stream);
+
 /* Adjoint of the squared-distance part: gx[p,i,:] = 2s * sum_j Cbar[p,i,j] (x_i - y_j),
  * gy[p,j,:] = 2s * sum_i Cbar[p,i,j] (y_j - x_i).  gx / gy may be NULL (not needed). */
 size_t kccot_cost_bwd_workspace_bytes(int nprob, int Bx, int By, long long K);

@@ -25,6 +25,7 @@ SIGNATURES = {
     "kccot_cost_fwd": (_I, [_P, _P, _I, _I, _I, _LL, _P, _P, _P, _P, _I, _I, _F, _P, _P, _SZ, _I, _P]),
     "kccot_mixed_cost_workspace_bytes": (_SZ, [_I, _I, _LL]),
     "kccot_mixed_cost_fwd": (_I, [_P, _P, _I, _I, _LL, _P, _P, _P, _P, _I, _I, _F, _P, _P, _SZ, _I, _P]),
+    "kccot_mixed_sqdist_partials": (_I, [_P, _P, _I, _I, _LL, _P, _SZ, _I, _P]),
     "kccot_cost_bwd_workspace_bytes": (_SZ, [_I, _I, _I, _LL]),
     "kccot_cost_bwd": (_I, [_P, _P, _P, _I, _I, _I, _LL, _F, _P, _P, _P, _SZ, _I, _P]),
     "kccot_martingale_bwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _F, _P, _P, _I, _P]),

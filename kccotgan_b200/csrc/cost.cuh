@@ -39,11 +39,13 @@ void tc_sqdist_plan(int nprob, int R, long long K, int* ksplit, int* kblocks_per
 int launch_sqdist_partials_tc(const float* x, const float* y, int nprob, int Bx, int By, long long K,
                               int ksplit, int kblocks_per_slab, float* part, cudaStream_t st);
 
-// grad_tcgen05.cu — out[p,r,:] (+)= 2s * sum_c W[p,r,c] * (z[p,r,:] - z[p,c,:]) over the stacked
-// rows z = [x; y]; W [nprob,128,128] (zero padded).  gx / gy may be null.
+// grad_tcgen05.cu — tensor-core adjoint over the stacked rows z = [x; y] (see the file header).
+// Wws: [nprob, R, R] fp32 scratch for the weight matrix.  gx / gy may be null.
 bool tc_grad_supported(const float* x, const float* y, int Bx, int By, long long K, const float* gx,
                        const float* gy);
-int launch_grad_tc(const float* W, const float* x, const float* y, int nprob, int Bx, int By, long long K,
-                   float s, float* gx, float* gy, int accumulate, cudaStream_t st);
+int launch_grad_tc(const float* Cbar3, const float* x, const float* y, int nprob, int Bx, int By, long long K,
+                   float s, float* gx, float* gy, int accumulate, float* Wws, cudaStream_t st);
+int launch_grad_pair_tc(const float* Cbar, const float* x, const float* y, int nprob, int Bx, int By, long long K,
+                        float s, float* gx, float* gy, int accumulate, float* Wws, cudaStream_t st);
 
 }  // namespace kccot

@@ -148,6 +148,36 @@ int kccot_mixed_cost_fwd(const float* real, const float* fake, int nprob, int B,
   return launch_cost_finalize(blocks, 3, nprob, T, J, s, st);
 }
 
+int kccot_mixed_sqdist_partials(const float* real, const float* fake, int nprob, int B, long long K, void* ws,
+                                size_t ws_bytes, int flags, void* stream) {
+  if (int rc = check_common(nprob, B, B, K)) return rc;
+  KCCOT_CHECK_ARG(real && fake && ws, "null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool tc_ok = (real != fake) && tc_sqdist_supported(real, fake, B, B, K);
+  const int path = pick_path(flags, tc_ok);
+  if (path < 0) {
+    set_error("tcgen05 path requested but unsupported for B=%d K=%lld", B, K);
+    return KCCOT_EUNSUPPORTED;
+  }
+  if (path == KCCOT_PATH_TCGEN05) {
+    int ks, kbps;
+    tc_sqdist_plan(nprob, 2 * B, K, &ks, &kbps);
+    KCCOT_CHECK_ARG(ws_bytes >= (size_t)nprob * ks * kTcTile * 4, "workspace too small");
+    return launch_sqdist_partials_tc(real, fake, nprob, B, B, K, ks, kbps, (float*)ws, st);
+  }
+  int ks;
+  long long slab;
+  choose_ksplit_simt(nprob, B, B, K, &ks, &slab);
+  const size_t one = align_up((size_t)nprob * ks * B * B * 4, 256);
+  KCCOT_CHECK_ARG(ws_bytes >= 3 * one, "workspace too small");
+  const float* xs[3] = {real, real, fake};
+  const float* ys[3] = {fake, real, fake};
+  for (int q = 0; q < 3; ++q)
+    if (int rc = launch_sqdist_partials_simt(xs[q], ys[q], nprob, B, B, K, ks, slab, (float*)((char*)ws + q * one), st))
+      return rc;
+  return KCCOT_OK;
+}
+
 size_t kccot_cost_bwd_workspace_bytes(int nprob, int Bx, int By, long long K) {
   (void)K;
   return align_up((size_t)(nprob > 0 ? nprob : 1) * 128 * 128 * sizeof(float) * (Bx + By <= 128 ? 1 : 0) + 256, 256);
@@ -155,12 +185,18 @@ size_t kccot_cost_bwd_workspace_bytes(int nprob, int Bx, int By, long long K) {
 
 int kccot_cost_bwd(const float* Cbar, const float* x, const float* y, int nprob, int Bx, int By, long long K, float s,
                    float* gx, float* gy, void* ws, size_t ws_bytes, int flags, void* stream) {
-  (void)ws; (void)ws_bytes;
   if (int rc = check_common(nprob, Bx, By, K)) return rc;
   KCCOT_CHECK_ARG(Cbar && x && y, "null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   const int acc = (flags & KCCOT_FLAG_ACCUMULATE) ? 1 : 0;
   const long long cprob = (long long)Bx * By;
+  const bool tc_ok = (flags & 3) != KCCOT_PATH_SIMT && x != y && gx != gy && ws &&
+                     ws_bytes >= (size_t)nprob * 128 * 128 * 4 && tc_grad_supported(x, y, Bx, By, K, gx, gy);
+  if ((flags & 3) == KCCOT_PATH_TCGEN05 && !tc_ok) {
+    set_error("tcgen05 gradient path requested but unsupported for Bx=%d By=%d K=%lld", Bx, By, K);
+    return KCCOT_EUNSUPPORTED;
+  }
+  if (tc_ok) return launch_grad_pair_tc(Cbar, x, y, nprob, Bx, By, K, s, gx, gy, acc, (float*)ws, st);
   if (gx)
     if (int rc = launch_cost_bwd_simt(Cbar, By, 1, cprob, x, y, nprob, Bx, By, K, s, gx, acc, st)) return rc;
   if (gy)
@@ -204,7 +240,7 @@ int kccot_mixed_cost_bwd(const float* Cbar3, const float* real, const float* fak
     return KCCOT_EUNSUPPORTED;
   }
   if (tc_ok) {
-    if (int rc = launch_grad_tc(Cbar3, real, fake, nprob, B, B, K, s, g_real, g_fake, acc, st)) return rc;
+    if (int rc = launch_grad_tc(Cbar3, real, fake, nprob, B, B, K, s, g_real, g_fake, acc, (float*)ws, st)) return rc;
   } else {
     if (g_fake) {
       if (int rc = launch_cost_bwd_simt(Cxy, 1, B, cprob, fake, real, nprob, B, B, K, s, g_fake, acc, st)) return rc;

@@ -102,12 +102,14 @@ __global__ void __launch_bounds__(256) cost_finalize_kernel(CostBlocks blocks, i
   const int j = (int)(idx % b.By);
   const int i = (int)((idx / b.By) % b.Bx);
   const int p = (int)(idx / ((long long)b.Bx * b.By));
-  float d = 0.f;
+  // the split-K partials are summed in fp64: a sequential fp32 sum of ~150-300 partials of a value
+  // near 1e4 would by itself cost ~5e-4 absolute on C, more than the whole fp32 budget of the path
+  double d = 0.0;
   if (!(b.zero_diag && i == j)) {
     const float* pp = b.part + (long long)p * b.prob_stride + (long long)(b.row_off + i) * b.ld + b.col_off + j;
-    for (int ks = 0; ks < b.nks; ++ks) d += pp[(long long)ks * b.ks_stride];
+    for (int ks = 0; ks < b.nks; ++ks) d += (double)pp[(long long)ks * b.ks_stride];
   }
-  float hm = 0.f;
+  double hm = 0.0;
   const int tj = (T - 1) * J;
   for (int pair = 0; pair < 2; ++pair) {
     const float* h = pair ? b.h2 : b.h1;
@@ -117,9 +119,9 @@ __global__ void __launch_bounds__(256) cost_finalize_kernel(CostBlocks blocks, i
     const float* Mr = M + ((long long)p * b.By + j) * T * J;
     float a = 0.f;
     for (int q = 0; q < tj; ++q) a = fmaf(hr[q], Mr[q + J] - Mr[q], a);
-    hm += a;
+    hm += (double)a;
   }
-  b.C[(long long)p * b.C_prob_stride + (long long)i * b.By + j] = s * d + s * hm;
+  b.C[(long long)p * b.C_prob_stride + (long long)i * b.By + j] = (float)((double)s * (d + hm));
 }
 
 int launch_cost_finalize(const CostBlocks& blocks, int nblocks, int nprob, int T, int J, float s,

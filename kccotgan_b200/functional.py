@@ -116,7 +116,7 @@ class CostFn(torch.autograd.Function):
                 gy = torch.empty_like(Y) if need[1] else None
                 ws = _ws(_lib.load().kccot_cost_bwd_workspace_bytes(1, Bx, By, K), dev)
                 _lib.call("kccot_cost_bwd", _ptr(gC), _ptr(X), _ptr(Y), 1, Bx, By, K, s, _ptr(gx), _ptr(gy),
-                          _ptr(ws), ws.numel(), 0, st)
+                          _ptr(ws), ws.numel(), _PATH["flags"] if not same else _lib.PATH_SIMT, st)
             gout = [None, None, None, None]
             for q, (h, M) in enumerate(pairs):
                 if h is None or not (need[2 + 2 * q] or need[3 + 2 * q]):
