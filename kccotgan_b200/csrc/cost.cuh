@@ -19,6 +19,22 @@ struct CostBlocks {
   CostBlock b[3];
 };
 
+// One output tensor of the martingale adjoint (see martingale_bwd_kernel).
+struct MartJob {
+  float* out;                 // [nprob, nrows, T, J]; null = skip
+  const float *C1, *X1;       // first product: weights from Cbar matrix C1, factors from X1 [nprob, ncontr, T, J]
+  const float *C2, *X2;       // optional second product
+  long long cprob;            // elements between problems in C1 / C2
+  int ld, nrows, ncontr;      // Cbar leading dimension; output rows; contraction length
+  int transposed;             // 0: W[r,k] = C[r*ld + k];  1: W[r,k] = C[k*ld + r]
+  int mode;                   // 0: factors are first differences of M;  1: shifted differences of h
+  int acc;                    // add into `out`
+};
+struct MartJobs {
+  MartJob j[4];
+};
+int launch_martingale_jobs(const MartJobs& jobs, int njobs, int nprob, int T, int J, float s, cudaStream_t st);
+
 // cost_simt.cu
 void choose_ksplit_simt(int nprob, int Bx, int By, long long K, int* ksplit, long long* kslab);
 int launch_sqdist_partials_simt(const float* x, const float* y, int nprob, int Bx, int By, long long K,

@@ -253,18 +253,14 @@ int kccot_mixed_cost_bwd(const float* Cbar3, const float* real, const float* fak
       if (int rc = launch_cost_bwd_simt(Cxx, 1, B, cprob, real, real, nprob, B, B, K, s, g_real, 1, st)) return rc;
     }
   }
-  // martingale terms: xy = (h_fake, m_real), xx = (h_real, m_real), yy = (h_fake, m_fake)
-  if (gh_fake || gm_real)
-    if (int rc = launch_martingale_bwd(Cxy, cprob, h_fake, m_real, nprob, B, B, T, J, s, 1.f, gh_fake, gm_real, acc, acc, st))
-      return rc;
-  if (gh_real || gm_real)
-    if (int rc = launch_martingale_bwd(Cxx, cprob, h_real, m_real, nprob, B, B, T, J, s, 1.f, gh_real, gm_real, acc,
-                                       1, st))
-      return rc;
-  if (gh_fake || gm_fake)
-    if (int rc = launch_martingale_bwd(Cyy, cprob, h_fake, m_fake, nprob, B, B, T, J, s, 1.f, gh_fake, gm_fake, 1,
-                                       acc, st))
-      return rc;
+  // martingale terms: xy = (h_fake, m_real), xx = (h_real, m_real), yy = (h_fake, m_fake) — one launch
+  MartJobs jobs{};
+  const int Bi = B;
+  jobs.j[0] = MartJob{gh_fake, Cxy, m_real, Cyy, m_fake, cprob, Bi, Bi, Bi, 0, 0, acc};
+  jobs.j[1] = MartJob{gm_real, Cxy, h_fake, Cxx, h_real, cprob, Bi, Bi, Bi, 1, 1, acc};
+  jobs.j[2] = MartJob{gh_real, Cxx, m_real, nullptr, nullptr, cprob, Bi, Bi, Bi, 0, 0, acc};
+  jobs.j[3] = MartJob{gm_fake, Cyy, h_fake, nullptr, nullptr, cprob, Bi, Bi, Bi, 1, 1, acc};
+  if (int rc = launch_martingale_jobs(jobs, 4, nprob, T, J, s, st)) return rc;
   return KCCOT_OK;
 }
 

@@ -93,42 +93,49 @@ void choose_ksplit_simt(int nprob, int Bx, int By, long long K, int* ksplit, lon
 // ---------------------------------------------------------------------------------------------
 // C = s * sum_ks P + s * sum_pairs h_row . DeltaM_col
 // ---------------------------------------------------------------------------------------------
+constexpr int FL = 8;   // lanes cooperating on one output element
+
 __global__ void __launch_bounds__(256) cost_finalize_kernel(CostBlocks blocks, int nprob, int T, int J,
                                                             float s) {
   const CostBlock& b = blocks.b[blockIdx.z];
   const long long n = (long long)nprob * b.Bx * b.By;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= n) return;
-  const int j = (int)(idx % b.By);
-  const int i = (int)((idx / b.By) % b.Bx);
-  const int p = (int)(idx / ((long long)b.Bx * b.By));
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long idx = gid / FL;
+  const int sub = (int)(gid % FL);
+  const bool live = idx < n;
+  const int j = live ? (int)(idx % b.By) : 0;
+  const int i = live ? (int)((idx / b.By) % b.Bx) : 0;
+  const int p = live ? (int)(idx / ((long long)b.Bx * b.By)) : 0;
   // the split-K partials are summed in fp64: a sequential fp32 sum of ~150-300 partials of a value
   // near 1e4 would by itself cost ~5e-4 absolute on C, more than the whole fp32 budget of the path
   double d = 0.0;
-  if (!(b.zero_diag && i == j)) {
+  if (live && !(b.zero_diag && i == j)) {
     const float* pp = b.part + (long long)p * b.prob_stride + (long long)(b.row_off + i) * b.ld + b.col_off + j;
-    for (int ks = 0; ks < b.nks; ++ks) d += (double)pp[(long long)ks * b.ks_stride];
+    for (int ks = sub; ks < b.nks; ks += FL) d += (double)pp[(long long)ks * b.ks_stride];
   }
-  double hm = 0.0;
   const int tj = (T - 1) * J;
-  for (int pair = 0; pair < 2; ++pair) {
-    const float* h = pair ? b.h2 : b.h1;
-    const float* M = pair ? b.M2 : b.M1;
-    if (h == nullptr) continue;
-    const float* hr = h + ((long long)p * b.Bx + i) * T * J;
-    const float* Mr = M + ((long long)p * b.By + j) * T * J;
-    float a = 0.f;
-    for (int q = 0; q < tj; ++q) a = fmaf(hr[q], Mr[q + J] - Mr[q], a);
-    hm += (double)a;
+  float a = 0.f;
+  if (live) {
+    for (int pair = 0; pair < 2; ++pair) {
+      const float* h = pair ? b.h2 : b.h1;
+      const float* M = pair ? b.M2 : b.M1;
+      if (h == nullptr) continue;
+      const float* hr = h + ((long long)p * b.Bx + i) * T * J;
+      const float* Mr = M + ((long long)p * b.By + j) * T * J;
+      for (int q = sub; q < tj; q += FL) a = fmaf(hr[q], Mr[q + J] - Mr[q], a);
+    }
   }
-  b.C[(long long)p * b.C_prob_stride + (long long)i * b.By + j] = (float)((double)s * (d + hm));
+  d += (double)a;
+#pragma unroll
+  for (int o = FL / 2; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+  if (live && sub == 0) b.C[(long long)p * b.C_prob_stride + (long long)i * b.By + j] = (float)((double)s * d);
 }
 
 int launch_cost_finalize(const CostBlocks& blocks, int nblocks, int nprob, int T, int J, float s,
                          cudaStream_t st) {
   long long nmax = 0;
   for (int i = 0; i < nblocks; ++i) nmax = max(nmax, (long long)nprob * blocks.b[i].Bx * blocks.b[i].By);
-  dim3 grid((unsigned)((nmax + 255) / 256), 1, nblocks);
+  dim3 grid((unsigned)((nmax * FL + 255) / 256), 1, nblocks);
   cost_finalize_kernel<<<grid, 256, 0, st>>>(blocks, nprob, T, J, s);
   KCCOT_LAUNCH_CHECK();
   return KCCOT_OK;
@@ -215,57 +222,65 @@ int launch_cost_bwd_simt(const float* W, long long sr, long long sc, long long w
 }
 
 // ---------------------------------------------------------------------------------------------
-// martingale adjoint (one (h, M) pair against one Cbar [Bx,By])
-//   gh[i,t,c] = s * sum_j Cbar[i,j] * (M[j,t+1,c] - M[j,t,c])   (t < T-1; 0 at t = T-1)
-//   gM[j,t,c] = s * sum_i Cbar[i,j] * (h[i,t-1,c] [t>=1] - h[i,t,c] [t<=T-2])
+// martingale adjoint: up to 4 output tensors in one launch, each the sum of up to two products
+//   out[p,r,q] (+)= s * sum_k W1[r,k] F1[k,q] (+ s * sum_k W2[r,k] F2[k,q]),  q = (t, c)
+//   W[r,k] = Cbar[r*ld + k] or (transposed) Cbar[k*ld + r]
+//   F mode 0 (gradient of h, F from M): M[k,t+1,c] - M[k,t,c] for t < T-1, else 0
+//   F mode 1 (gradient of M, F from h): h[k,t-1,c] [t>=1] - h[k,t,c] [t<=T-2]
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) martingale_bwd_kernel(const float* __restrict__ Cbar, long long cprob,
-                                                             const float* __restrict__ h,
-                                                             const float* __restrict__ M, int nprob, int Bx,
-                                                             int By, int T, int J, float s, float w,
-                                                             float* __restrict__ gh, float* __restrict__ gM,
-                                                             int acc_h, int acc_M) {
-  const long long nh = (long long)nprob * Bx * T * J, nM = (long long)nprob * By * T * J;
-  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ float mart_factor(const float* X, int mode, int t, int T, int J, int q) {
+  if (mode == 0) return (t < T - 1) ? X[q + J] - X[q] : 0.f;
+  return ((t >= 1) ? X[q - J] : 0.f) - ((t <= T - 2) ? X[q] : 0.f);
+}
+
+__global__ void __launch_bounds__(128) martingale_bwd_kernel(MartJobs jobs, int T, int J, float s) {
+  extern __shared__ float wrow[];      // [2][ncontr]
+  const MartJob& jb = jobs.j[blockIdx.y];
+  const int r = blockIdx.x, p = blockIdx.z;
+  if (r >= jb.nrows || jb.out == nullptr) return;
   const int TJ = T * J;
-  if (idx < nh) {
-    if (gh == nullptr) return;
-    const int c = (int)(idx % J), t = (int)((idx / J) % T);
-    const int i = (int)((idx / TJ) % Bx), p = (int)(idx / ((long long)TJ * Bx));
+  for (int src = 0; src < 2; ++src) {
+    const float* C = src ? jb.C2 : jb.C1;
+    if (C == nullptr) continue;
+    C += (long long)p * jb.cprob;
+    for (int k = threadIdx.x; k < jb.ncontr; k += blockDim.x)
+      wrow[src * jb.ncontr + k] = jb.transposed ? C[(long long)k * jb.ld + r] : C[(long long)r * jb.ld + k];
+  }
+  __syncthreads();
+  float* out = jb.out + ((long long)p * jb.nrows + r) * TJ;
+  for (int q = threadIdx.x; q < TJ; q += blockDim.x) {
+    const int t = q / J;
     float a = 0.f;
-    if (t < T - 1) {
-      const float* cb = Cbar + (long long)p * cprob + (long long)i * By;
-      const float* Mp = M + (long long)p * By * TJ + t * J + c;
-      for (int j = 0; j < By; ++j) a = fmaf(cb[j], Mp[(long long)j * TJ + J] - Mp[(long long)j * TJ], a);
+    for (int src = 0; src < 2; ++src) {
+      const float* X = src ? jb.X2 : jb.X1;
+      if ((src ? jb.C2 : jb.C1) == nullptr) continue;
+      X += (long long)p * jb.ncontr * TJ;
+      const float* w = wrow + src * jb.ncontr;
+      for (int k = 0; k < jb.ncontr; ++k) a = fmaf(w[k], mart_factor(X + (long long)k * TJ, jb.mode, t, T, J, q), a);
     }
-    const float v = w * s * a;
-    gh[idx] = acc_h ? gh[idx] + v : v;
-    return;
+    const float v = s * a;
+    out[q] = jb.acc ? out[q] + v : v;
   }
-  idx -= nh;
-  if (idx >= nM || gM == nullptr) return;
-  const int c = (int)(idx % J), t = (int)((idx / J) % T);
-  const int j = (int)((idx / TJ) % By), p = (int)(idx / ((long long)TJ * By));
-  const float* cb = Cbar + (long long)p * cprob + j;
-  const float* hp = h + (long long)p * Bx * TJ + t * J + c;
-  float a = 0.f;
-  for (int i = 0; i < Bx; ++i) {
-    const float hprev = (t >= 1) ? hp[(long long)i * TJ - J] : 0.f;
-    const float hcur = (t <= T - 2) ? hp[(long long)i * TJ] : 0.f;
-    a = fmaf(cb[(long long)i * By], hprev - hcur, a);
-  }
-  const float v = w * s * a;
-  gM[idx] = acc_M ? gM[idx] + v : v;
+}
+
+int launch_martingale_jobs(const MartJobs& jobs, int njobs, int nprob, int T, int J, float s, cudaStream_t st) {
+  int maxrows = 0, maxc = 0;
+  for (int i = 0; i < njobs; ++i) { maxrows = max(maxrows, jobs.j[i].nrows); maxc = max(maxc, jobs.j[i].ncontr); }
+  if (maxrows == 0) return KCCOT_OK;
+  dim3 grid(maxrows, njobs, nprob);
+  martingale_bwd_kernel<<<grid, 128, (size_t)2 * maxc * sizeof(float), st>>>(jobs, T, J, s);
+  KCCOT_LAUNCH_CHECK();
+  return KCCOT_OK;
 }
 
 int launch_martingale_bwd(const float* Cbar, long long cprob, const float* h, const float* M, int nprob,
                           int Bx, int By, int T, int J, float s, float w, float* gh, float* gM,
                           int acc_h, int acc_M, cudaStream_t st) {
-  const long long n = (long long)nprob * (Bx + By) * T * J;
-  martingale_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(Cbar, cprob, h, M, nprob, Bx, By, T, J, s,
-                                                                     w, gh, gM, acc_h, acc_M);
-  KCCOT_LAUNCH_CHECK();
-  return KCCOT_OK;
+  (void)w;
+  MartJobs jobs{};
+  jobs.j[0] = MartJob{gh, Cbar, M, nullptr, nullptr, cprob, By, Bx, By, 0, 0, acc_h};
+  jobs.j[1] = MartJob{gM, Cbar, h, nullptr, nullptr, cprob, By, By, Bx, 1, 1, acc_M};
+  return launch_martingale_jobs(jobs, 2, nprob, T, J, s, st);
 }
 
 }  // namespace kccot

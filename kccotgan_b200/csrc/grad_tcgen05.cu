@@ -5,9 +5,11 @@
 //     g_r = 2s * sum_c W_rc (z_r - z_c) = -2s * sum_c W'_rc z_c,   W' = W - diag(rowsum(W)),
 // i.e. a skinny GEMM  G^T[col, r] = sum_c Z[c, col] * W'[r, c]  streamed once over the video columns.
 //
-//   A operand = the TMA-loaded video tile itself, MN-major: a [rows x 32] fp32 box with 128-byte swizzle
-//               is exactly the canonical MN-major SW128 atom stack (8 contraction rows per 1024 B),
-//               4 boxes side by side give M = 128 video columns (LBO = box bytes).
+//   A operand = the TMA-loaded video tile itself, MN-major.  tcgen05 accepts exactly one shared-memory
+//               layout for MN-major 32-bit operands, SWIZZLE_128B_BASE32B (32-byte chunks XOR row%4,
+//               4-row atoms): the tiles are loaded with the matching TMA mode 128B_ATOM_32B, so a
+//               [rows x 32] box is a stack of canonical atoms (SBO = 512 B), and 4 boxes side by side
+//               give M = 128 video columns (LBO = box bytes).
 //   B operand = W' (K-major SW128), split tf32 hi/lo once per CTA and resident in shared memory.
 //   3xTF32:    D += Zhi.Whi + Zlo.Whi + Zhi.Wlo, fp32 accumulate in TMEM (2 accumulator buffers).
 //   Stages alternate between the x rows and the y rows of a 128-column tile (two TMA tensors).
@@ -183,8 +185,8 @@ grad_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ 
           for (int kk = 0; kk < rows / 8; ++kk) {
             const int c = c_off + kk * 8;                     // contraction index of this k-step
             const uint32_t woff = (uint32_t)((c >> 5) * wtile_bytes + (c & 31) * 4);
-            const uint64_t a_h = tc::make_smem_desc_sw128(ahi + kk * 1024, lbo, 1024);
-            const uint64_t a_l = tc::make_smem_desc_sw128(alo + kk * 1024, lbo, 1024);
+            const uint64_t a_h = tc::make_smem_desc(ahi + kk * 1024, lbo, 512, 1);
+            const uint64_t a_l = tc::make_smem_desc(alo + kk * 1024, lbo, 512, 1);
             const uint64_t b_h = tc::make_smem_desc_sw128(whi + woff, 16, 1024);
             const uint64_t b_l = tc::make_smem_desc_sw128(wlo + woff, 16, 1024);
             tc::umma_tf32(d_tmem, a_h, b_h, idesc, first ? 0u : 1u);
@@ -313,10 +315,10 @@ int launch_grad_tc(const float* Cbar3, const float* x, const float* y, int nprob
   KCCOT_LAUNCH_CHECK();
   CUtensorMap tmx, tmy;
   if (int rc = encode_tmap_3d(&tmx, x, (uint64_t)K, (uint64_t)Bx, (uint64_t)nprob, (uint64_t)K * 4, (uint64_t)K * 4 * Bx,
-                              kBoxCols, (uint32_t)Bx))
+                              kBoxCols, (uint32_t)Bx, true))
     return rc;
   if (int rc = encode_tmap_3d(&tmy, y, (uint64_t)K, (uint64_t)By, (uint64_t)nprob, (uint64_t)K * 4, (uint64_t)K * 4 * By,
-                              kBoxCols, (uint32_t)By))
+                              kBoxCols, (uint32_t)By, true))
     return rc;
   if (gy)
     if (int rc = launch_grad_rows(tmx, tmy, Wws, nprob, Bx, By, K, s, Bx, By, gy, accumulate, st)) return rc;
@@ -332,10 +334,10 @@ int launch_grad_pair_tc(const float* Cbar, const float* x, const float* y, int n
   KCCOT_LAUNCH_CHECK();
   CUtensorMap tmx, tmy;
   if (int rc = encode_tmap_3d(&tmx, x, (uint64_t)K, (uint64_t)Bx, (uint64_t)nprob, (uint64_t)K * 4, (uint64_t)K * 4 * Bx,
-                              kBoxCols, (uint32_t)Bx))
+                              kBoxCols, (uint32_t)Bx, true))
     return rc;
   if (int rc = encode_tmap_3d(&tmy, y, (uint64_t)K, (uint64_t)By, (uint64_t)nprob, (uint64_t)K * 4, (uint64_t)K * 4 * By,
-                              kBoxCols, (uint32_t)By))
+                              kBoxCols, (uint32_t)By, true))
     return rc;
   if (gy)
     if (int rc = launch_grad_rows(tmx, tmy, Wws, nprob, Bx, By, K, s, Bx, By, gy, accumulate, st)) return rc;

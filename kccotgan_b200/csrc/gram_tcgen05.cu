@@ -7,7 +7,12 @@
 //   8 convert warps: per k-block subtract the column mean (squared distance is translation
 //                    invariant; centring removes the cancellation between |x|^2+|y|^2 and 2x.y),
 //                    accumulate the fp32 row norms, split into tf32 hi + tf32 lo in place.
-//   MMA thread    : D += hi.hi^T + hi.lo^T + lo.hi^T   (3xTF32, fp32 accumulate in TMEM).
+//   MMA thread    : D += hi.hi^T + hi.lo^T + lo.hi^T   (3xTF32, fp32 accumulate in TMEM).  The tensor
+//                    core's fp32 accumulation truncates, so a long chain into one large accumulator
+//                    (e.g. D_ii ~ |x_i|^2 for a fake that resembles its real) picks up a bias that grows
+//                    with chain length x magnitude.  The hi.hi products are therefore dealt round-robin
+//                    to three TMEM accumulators and the (2^-11 smaller) cross products go to a fourth;
+//                    the epilogue adds the four in fp32 (measured: 9x smaller error on video-like data).
 //   epilogue      : P_ij = n_i + n_j - 2 D_ij  ->  part[p][ks][128][128]  (partial squared distances;
 //                    cost_finalize_kernel sums the slabs and adds the martingale terms).
 #include "cost.cuh"
@@ -23,7 +28,8 @@ constexpr int kStages = 4;
 constexpr int kConvWarps = 8;
 constexpr int kConvThreads = kConvWarps * 32;
 constexpr int kThreads = 64 + kConvThreads;     // warp 0 TMA, warp 1 MMA, warps 2.. convert/epilogue
-constexpr int kTmemCols = 128;
+constexpr int kTmemCols = 512;                 // 4 accumulators of up to 128 columns
+constexpr int kNumAcc = 4;
 
 struct __align__(1024) Smem {
   uint8_t hi[kStages][kTileBytes];
@@ -107,9 +113,10 @@ sqdist_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
           for (int k4 = 0; k4 < kKB / 8; ++k4) {
             const uint64_t dh = tc::make_smem_desc_sw128(hi_addr + k4 * 32, 16, 1024);
             const uint64_t dl = tc::make_smem_desc_sw128(lo_addr + k4 * 32, 16, 1024);
-            tc::umma_tf32(tmem, dh, dh, idesc, (kb > kb0 || k4 > 0) ? 1u : 0u);
-            tc::umma_tf32(tmem, dh, dl, idesc, 1u);
-            tc::umma_tf32(tmem, dl, dh, idesc, 1u);
+            const int step = (kb - kb0) * (kKB / 8) + k4;
+            tc::umma_tf32(tmem + (uint32_t)((step % 3) * kRows), dh, dh, idesc, step >= 3 ? 1u : 0u);
+            tc::umma_tf32(tmem + (uint32_t)(3 * kRows), dh, dl, idesc, step > 0 ? 1u : 0u);
+            tc::umma_tf32(tmem + (uint32_t)(3 * kRows), dl, dh, idesc, 1u);
           }
           tc::umma_commit(&S.empty[stage]);
           if (kb == kb1 - 1) tc::umma_commit(&S.acc_full);
@@ -210,6 +217,15 @@ sqdist_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
           float d[32];
           tc::tmem_ld_32x32(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, d);
           tc::tmem_ld_wait();
+          const int nacc_used = min(kNumAcc - 1, (kb1 - kb0) * (kKB / 8));
+          for (int a = 1; a < kNumAcc; ++a) {
+            if (a < kNumAcc - 1 && a >= nacc_used) continue;      // accumulator never written in this item
+            float t[32];
+            tc::tmem_ld_32x32(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(a * kRows + c0), t);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) d[j] += t[j];
+          }
           if (row < R) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
@@ -254,7 +270,7 @@ static PFN_encodeTiled get_encode() {
 }
 
 int encode_tmap_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
-                   uint64_t stride2_bytes, uint32_t b0, uint32_t b1) {
+                   uint64_t stride2_bytes, uint32_t b0, uint32_t b1, bool atom32) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled entry point not available");
@@ -265,7 +281,8 @@ int encode_tmap_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1,
   cuuint32_t box[3] = {b0, b1, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with CUresult %d (dims %llu x %llu x %llu, box %u x %u)", (int)r,

@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(NT) stream_bwd_seed_kernel(const float* __rest
     float acc = 0.f;
     for (int j = lane; j < B; j += 32) {
       const float ch = (row[j] - shift) * kscale;
-      const float ce = row[j] * inv_eps;
+      const float ce = (row[j] - shift) * inv_eps;      // shifted cost: sum(pi) == 1 has zero gradient
       const float pi = g * fast_exp2(ui + v[j] - ch);
       grow[j] = pi * (1.f - ce);
       acc = fmaf(pi, ce, acc);
@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(NT) stream_bwd_seed_kernel(const float* __rest
     const float vj = v[j];
     for (int rr = 0; rr < nrows; ++rr) {
       const float c = C[(long long)(r0 + rr) * B + j];
-      acc = fmaf(g * fast_exp2(us[rr] + vj - (c - shift) * kscale), c * inv_eps, acc);
+      acc = fmaf(g * fast_exp2(us[rr] + vj - (c - shift) * kscale), (c - shift) * inv_eps, acc);
     }
     colsum_part[(long long)blockIdx.x * B + j] = acc;
   }

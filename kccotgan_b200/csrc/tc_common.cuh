@@ -115,14 +115,20 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // Shared-memory matrix descriptor (64 bit):
 //   [0,14) start address >> 4   [16,30) leading byte offset >> 4   [32,46) stride byte offset >> 4
 //   [46,48) version = 1 (sm_100)   [49,52) base offset = 0   [61,64) layout: 2 = SWIZZLE_128B
-__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+//   layout types: 2 = SWIZZLE_128B (16-byte chunks XOR row%8), 1 = SWIZZLE_128B_BASE32B (32-byte chunks
+//   XOR row%4 — the ONLY layout tcgen05 accepts for MN-major 32-bit (tf32) operands)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                   uint32_t layout_type) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3FFF);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)layout_type << 61;
   return d;
+}
+__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return make_smem_desc(saddr, lbo_bytes, sbo_bytes, 2);
 }
 // Instruction descriptor for kind::tf32, fp32 accumulate:
 //   [4,6) D format: 1 = F32   [7,10) A format: 2 = TF32   [10,13) B format: 2 = TF32
@@ -160,8 +166,9 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 
 }  // namespace tc
 
-// host: encode a 3-D fp32 tensor map [d2][d1][d0] with a (b0, b1, 1) box and 128-byte swizzle
+// host: encode a 3-D fp32 tensor map [d2][d1][d0] with a (b0, b1, 1) box; atom32 = false: 128-byte swizzle
+// with 16-byte atoms (K-major operands), true: 128-byte swizzle with 32-byte atoms (MN-major tf32 operands)
 int encode_tmap_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
-                   uint64_t stride2_bytes, uint32_t b0, uint32_t b1);
+                   uint64_t stride2_bytes, uint32_t b0, uint32_t b1, bool atom32 = false);
 
 }  // namespace kccot

@@ -77,3 +77,18 @@ for name in sys.argv[1:] or ["cfg1_mmnist", "cfg2_mazes"]:
     def skb():
         _lib.call("kccot_sinkhorn_bwd", F._ptr(C3), 3, B, 1.0, 100, F._ptr(uh), F._ptr(vh), F._ptr(nits), F._ptr(g), F._ptr(Cb), F._ptr(ws), 256, F._stream(C3.device))
     print(f"   sinkhorn fwd {timeit(skf):.1f} us   bwd {timeit(skb):.1f} us")
+
+    # tcgen05 vs CUDA-core gradients
+    outs = {}
+    for path in ("simt", "tcgen05"):
+        F.set_path(path)
+        lv = [inp[k].clone().requires_grad_(True) for k in INPUT_ORDER]
+        loss = gan_utils.compute_sinkhorn_loss(lv[0], lv[1], 1 / 15, 0.8, 100, *lv[2:], video=True)
+        try:
+            outs[path] = torch.autograd.grad(loss, lv[:2])
+        except Exception as e:
+            print("   grad", path, "failed:", e)
+    if len(outs) == 2:
+        for nm, a, b in zip(("g_real", "g_fake"), outs["simt"], outs["tcgen05"]):
+            print(f"   {nm}: |simt| {a.norm().item():.4e} |tc| {b.norm().item():.4e} rel diff {((a - b).norm() / a.norm()).item():.3e}")
+    F.set_path("auto")

@@ -191,7 +191,8 @@ def test_mixed_loss_full_size(gu, name, kind, path):
             e = rel_l2(flat[::st], g["grad_" + n + "_sample"])
             assert abs(np.linalg.norm(flat) - float(g["grad_" + n + "_norm"])) <= 1e-4 * float(g["grad_" + n + "_norm"])
             probe = np.random.default_rng(7).standard_normal(flat.size)
-            assert abs(flat @ probe - float(g["grad_" + n + "_proj"])) <= 2e-4 * float(g["grad_" + n + "_norm"]) * np.sqrt(flat.size) / 30
+            # a random projection sees every element: |<err, probe>| ~ ||err|| for a unit-variance probe
+            assert abs(flat @ probe - float(g["grad_" + n + "_proj"])) <= 5 * GRAD_TOL * float(g["grad_" + n + "_norm"])
         print("  grad", n, e)
         assert e < GRAD_TOL, (n, e)
 
