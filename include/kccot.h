@@ -117,6 +117,27 @@ int kccot_sinkhorn_bwd(const float* C, int nsolve, int B, float eps, int L, cons
                        void* ws, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Fused mixed Sinkhorn loss — gan_utils.py:204-227 (compute_sinkhorn_loss) in ONE call per direction:
+ *   fwd: stacked squared distances -> three cost matrices -> three Sinkhorn solves -> 2*xy - xx - yy
+ *   bwd: three reverse solves -> adjoint GEMMs -> gradients of real / fake / h_fake / m_real / h_real / m_fake
+ * `saved` (kccot_mixed_loss_saved_bytes) holds what the backward needs: C3 | u_hist | v_hist | nits | cost.
+ * loss [nprob]; terms [nprob,3] = (xy, xx, yy) (may be NULL).  gloss [nprob] on the device.
+ * Any gradient pointer may be NULL.  eps / L are explicit here: the reference's Python entry point
+ * always passes 1.0 / 100 (its eps/L arguments are swallowed).
+ * ------------------------------------------------------------------------------------------ */
+size_t kccot_mixed_loss_saved_bytes(int nprob, int B, int L);
+size_t kccot_mixed_loss_workspace_bytes(int nprob, int B, long long K, int L);
+int kccot_mixed_loss_fwd(const float* real, const float* fake, int nprob, int B, long long K,
+                         const float* h_fake, const float* m_real, const float* h_real,
+                         const float* m_fake, int T, int J, float s, float eps, int L, void* saved,
+                         float* loss, float* terms, void* ws, size_t ws_bytes, int flags, void* stream);
+int kccot_mixed_loss_bwd(const float* gloss, const float* real, const float* fake, int nprob, int B,
+                         long long K, const float* h_fake, const float* m_real, const float* h_real,
+                         const float* m_fake, int T, int J, float s, float eps, int L, const void* saved,
+                         float* g_real, float* g_fake, float* gh_fake, float* gm_real, float* gh_real,
+                         float* gm_fake, void* ws, size_t ws_bytes, int flags, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Martingale penalty p_M — gan_utils.py:179-201.  M [B,T,J]; pm [1]; gM [B,T,J] = gpm * dpm/dM.
  * ------------------------------------------------------------------------------------------ */
 int kccot_pm_fwd(const float* M, int B, int T, int J, float reg_lam, float s, float* pm,

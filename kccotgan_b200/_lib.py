@@ -35,6 +35,11 @@ SIGNATURES = {
     "kccot_sinkhorn_workspace_bytes": (_SZ, [_I, _I, _I]),
     "kccot_sinkhorn_fwd": (_I, [_P, _I, _I, _F, _I, _I, _F, _I, _P, _P, _P, _P, _P, _SZ, _P]),
     "kccot_sinkhorn_bwd": (_I, [_P, _I, _I, _F, _I, _P, _P, _P, _P, _P, _P, _SZ, _P]),
+    "kccot_mixed_loss_saved_bytes": (_SZ, [_I, _I, _I]),
+    "kccot_mixed_loss_workspace_bytes": (_SZ, [_I, _I, _LL, _I]),
+    "kccot_mixed_loss_fwd": (_I, [_P, _P, _I, _I, _LL, _P, _P, _P, _P, _I, _I, _F, _F, _I, _P, _P, _P, _P, _SZ, _I, _P]),
+    "kccot_mixed_loss_bwd": (_I, [_P, _P, _P, _I, _I, _LL, _P, _P, _P, _P, _I, _I, _F, _F, _I, _P, _P, _P, _P, _P, _P,
+                                  _P, _P, _SZ, _I, _P]),
     "kccot_pm_fwd": (_I, [_P, _I, _I, _I, _F, _F, _P, _P, _P]),
     "kccot_pm_bwd": (_I, [_P, _I, _I, _I, _F, _F, _P, _P, _P, _P]),
     "kccot_smooth_workspace_bytes": (_SZ, [_I, _I, _I, _I, _I, _I]),

@@ -84,7 +84,8 @@ grad_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ 
                long long K, const float* __restrict__ W, int row_off, int N, float neg2s, float* __restrict__ out,
                int accumulate, int nstages) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // align by OFFSET so that the compiler keeps the shared address space (LDS/STS, not generic LD/ST)
+  uint8_t* base = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int R = Bx + By;
   const int Npad = (N + 15) & ~15;
@@ -210,17 +211,18 @@ grad_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ 
         const int rows = half ? By : Bx;
         if (rows == 0) continue;
         tc::mbar_wait(&bars.full[stage], phase);
-        float4* hi = reinterpret_cast<float4*>(st_hi + (size_t)stage * stage_bytes);
-        float4* lo = reinterpret_cast<float4*>(st_lo + (size_t)stage * stage_bytes);
+        const uint32_t hi = tc::smem_u32(st_hi + (size_t)stage * stage_bytes);
+        const uint32_t lo = tc::smem_u32(st_lo + (size_t)stage * stage_bytes);
         const int n16 = 4 * rows * 8;                         // 16-byte units in this stage
+#pragma unroll 4
         for (int e = ct; e < n16; e += kConvThreads) {
-          const float4 v = hi[e];
+          const float4 v = tc::lds128(hi + e * 16);
           float4 h, l;
           h.x = tc::to_tf32(v.x); h.y = tc::to_tf32(v.y); h.z = tc::to_tf32(v.z); h.w = tc::to_tf32(v.w);
           l.x = tc::to_tf32(v.x - h.x); l.y = tc::to_tf32(v.y - h.y);
           l.z = tc::to_tf32(v.z - h.z); l.w = tc::to_tf32(v.w - h.w);
-          hi[e] = h;
-          lo[e] = l;
+          tc::sts128(hi + e * 16, h);
+          tc::sts128(lo + e * 16, l);
         }
         tc::fence_proxy_async_smem();
         __syncwarp();

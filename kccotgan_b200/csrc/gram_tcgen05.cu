@@ -6,7 +6,9 @@
 //   TMA warp      : fills a 4-stage ring.
 //   8 convert warps: per k-block subtract the column mean (squared distance is translation
 //                    invariant; centring removes the cancellation between |x|^2+|y|^2 and 2x.y),
-//                    accumulate the fp32 row norms, split into tf32 hi + tf32 lo in place.
+//                    accumulate the fp32 row norms, split into tf32 hi + tf32 lo in place.  Warp w
+//                    owns 16-byte chunk w of all 128 rows, so the column mean is a warp-shuffle
+//                    reduction and the only shared-memory traffic is tile in (16 KB) + hi/lo out (32 KB).
 //   MMA thread    : D += hi.hi^T + hi.lo^T + lo.hi^T   (3xTF32, fp32 accumulate in TMEM).  The tensor
 //                    core's fp32 accumulation truncates, so a long chain into one large accumulator
 //                    (e.g. D_ii ~ |x_i|^2 for a fake that resembles its real) picks up a bias that grows
@@ -24,7 +26,7 @@ namespace {
 constexpr int kRows = 128;
 constexpr int kKB = 32;                         // fp32 columns per k-block (one 128-B swizzle row)
 constexpr int kTileBytes = kRows * kKB * 4;     // 16 KB
-constexpr int kStages = 4;
+constexpr int kStages = 6;
 constexpr int kConvWarps = 8;
 constexpr int kConvThreads = kConvWarps * 32;
 constexpr int kThreads = 64 + kConvThreads;     // warp 0 TMA, warp 1 MMA, warps 2.. convert/epilogue
@@ -34,7 +36,7 @@ constexpr int kNumAcc = 4;
 struct __align__(1024) Smem {
   uint8_t hi[kStages][kTileBytes];
   uint8_t lo[kStages][kTileBytes];
-  float colsum[2][kConvWarps][kKB];
+  float nrm_part[kConvWarps][kRows];
   float nrm[kRows];
   uint64_t full[kStages], conv[kStages], empty[kStages];
   uint64_t acc_full, acc_empty;
@@ -46,7 +48,9 @@ __global__ void __launch_bounds__(kThreads, 1)
 sqdist_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy, int Bx, int By,
                  long long K, int nprob, int ksplit, int kbps, float* __restrict__ part) {
   extern __shared__ uint8_t smem_raw[];
-  Smem& S = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // align by OFFSET (not by integer round-trip of the pointer) so that the compiler keeps the shared
+  // address space and emits LDS/STS instead of generic LD/ST
+  Smem& S = *reinterpret_cast<Smem*>(smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int R = Bx + By;
   const int N = (R + 15) & ~15;
@@ -127,54 +131,47 @@ sqdist_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
     }
   } else {
     // ------------------------------- convert + epilogue ---------------------------------------
+    // Converter warp cw owns the 16-byte chunk (4 columns) cw of every row; lane l handles rows
+    // l, l+32, l+64, l+96.  A quarter-warp touches 8 consecutive rows, whose swizzled chunk positions
+    // are all different: conflict-free.  Column sums are a pure warp reduction (no smem, no barrier).
     const int ct = threadIdx.x - 64;
     const int cw = ct >> 5;
-    const int chunk = ct & 7;            // 16-byte chunk (4 columns) of the 128-byte row
-    const int rbase = ct >> 3;           // rows rbase + 32*m
+    const int chunk = cw;
     const float invR = 1.f / (float)R;
     int stage = 0, phase = 0, acc_phase = 0;
     for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
-      const int p = w / ksplit, ks = w % ksplit;
+      const int ks = w % ksplit;
       const int kb0 = ks * kbps, kb1 = min(nkb, kb0 + kbps);
       float nacc[4] = {0.f, 0.f, 0.f, 0.f};
       for (int kb = kb0; kb < kb1; ++kb) {
         tc::mbar_wait(&S.full[stage], phase);
-        uint8_t* hi = &S.hi[stage][0];
-        uint8_t* lo = &S.lo[stage][0];
+        const uint32_t hi = tc::smem_u32(&S.hi[stage][0]);
+        const uint32_t lo = tc::smem_u32(&S.lo[stage][0]);
         float4 v[4];
         float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
-          const int r = rbase + 32 * m;
+          const int r = lane + 32 * m;
           v[m] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (r < R) v[m] = *reinterpret_cast<const float4*>(hi + r * 128 + ((chunk ^ (r & 7)) << 4));
+          if (r < R) v[m] = tc::lds128(hi + r * 128 + ((chunk ^ (r & 7)) << 4));
           cs.x += v[m].x; cs.y += v[m].y; cs.z += v[m].z; cs.w += v[m].w;
         }
 #pragma unroll
-        for (int o = 8; o <= 16; o <<= 1) {
+        for (int o = 16; o > 0; o >>= 1) {
           cs.x += __shfl_xor_sync(0xffffffffu, cs.x, o);
           cs.y += __shfl_xor_sync(0xffffffffu, cs.y, o);
           cs.z += __shfl_xor_sync(0xffffffffu, cs.z, o);
           cs.w += __shfl_xor_sync(0xffffffffu, cs.w, o);
         }
-        float* csbuf = &S.colsum[kb & 1][0][0];
-        if (lane < 8) *reinterpret_cast<float4*>(csbuf + cw * kKB + lane * 4) = cs;
-        tc::named_bar_sync(1, kConvThreads);
-        float4 tot = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int q = 0; q < kConvWarps; ++q) {
-          const float4 t = *reinterpret_cast<const float4*>(csbuf + q * kKB + chunk * 4);
-          tot.x += t.x; tot.y += t.y; tot.z += t.z; tot.w += t.w;
-        }
         const long long col0 = (long long)kb * kKB + chunk * 4;
         float4 cen;     // column mean; 0 beyond K so that TMA's zero fill stays zero
-        cen.x = (col0 + 0 < K) ? tot.x * invR : 0.f;
-        cen.y = (col0 + 1 < K) ? tot.y * invR : 0.f;
-        cen.z = (col0 + 2 < K) ? tot.z * invR : 0.f;
-        cen.w = (col0 + 3 < K) ? tot.w * invR : 0.f;
+        cen.x = (col0 + 0 < K) ? cs.x * invR : 0.f;
+        cen.y = (col0 + 1 < K) ? cs.y * invR : 0.f;
+        cen.z = (col0 + 2 < K) ? cs.z * invR : 0.f;
+        cen.w = (col0 + 3 < K) ? cs.w * invR : 0.f;
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
-          const int r = rbase + 32 * m;
+          const int r = lane + 32 * m;
           if (r < R) {
             const float a0 = v[m].x - cen.x, a1 = v[m].y - cen.y, a2 = v[m].z - cen.z, a3 = v[m].w - cen.w;
             nacc[m] = fmaf(a0, a0, fmaf(a1, a1, fmaf(a2, a2, fmaf(a3, a3, nacc[m]))));
@@ -183,8 +180,8 @@ sqdist_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
             l.x = tc::to_tf32(a0 - h.x); l.y = tc::to_tf32(a1 - h.y);
             l.z = tc::to_tf32(a2 - h.z); l.w = tc::to_tf32(a3 - h.w);
             const int off = r * 128 + ((chunk ^ (r & 7)) << 4);
-            *reinterpret_cast<float4*>(hi + off) = h;
-            *reinterpret_cast<float4*>(lo + off) = l;
+            tc::sts128(hi + off, h);
+            tc::sts128(lo + off, l);
           }
         }
         tc::fence_proxy_async_smem();
@@ -194,13 +191,13 @@ sqdist_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
       }
       // ---- epilogue: row norms -> smem, accumulator -> registers -> partial distances ----------
 #pragma unroll
-      for (int m = 0; m < 4; ++m) {
-        float a = nacc[m];
-        a += __shfl_xor_sync(0xffffffffu, a, 1);
-        a += __shfl_xor_sync(0xffffffffu, a, 2);
-        a += __shfl_xor_sync(0xffffffffu, a, 4);
-        const int r = rbase + 32 * m;
-        if (chunk == 0 && r < R) S.nrm[r] = a;
+      for (int m = 0; m < 4; ++m) S.nrm_part[cw][lane + 32 * m] = nacc[m];
+      tc::named_bar_sync(1, kConvThreads);
+      if (ct < kRows) {
+        float a = 0.f;
+#pragma unroll
+        for (int q = 0; q < kConvWarps; ++q) a += S.nrm_part[q][ct];      // fixed order: deterministic
+        S.nrm[ct] = a;
       }
       tc::named_bar_sync(1, kConvThreads);
       tc::mbar_wait(&S.acc_full, acc_phase);
@@ -270,7 +267,7 @@ static PFN_encodeTiled get_encode() {
 }
 
 int encode_tmap_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
-                   uint64_t stride2_bytes, uint32_t b0, uint32_t b1, bool atom32) {
+                   uint64_t stride2_bytes, uint32_t b0, uint32_t b1, bool atom32, bool noswizzle) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled entry point not available");
@@ -281,7 +278,9 @@ int encode_tmap_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1,
   cuuint32_t box[3] = {b0, b1, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   noswizzle ? CU_TENSOR_MAP_SWIZZLE_NONE
+                             : (atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B),
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {

@@ -1,19 +1,37 @@
-// Log-domain Sinkhorn for B <= 64: one CTA per problem, the cost matrix held in REGISTERS in both
-// row-major and column-major slices for all L iterations (gan_utils.py:151-164), and the fully
-// unrolled reverse pass with the adjoint of C accumulated in registers.
+// Sinkhorn for B <= 64: one CTA per problem, everything on chip for all L iterations
+// (gan_utils.py:151-164), and the fully unrolled reverse pass with the
+// adjoint of C accumulated in registers.
 //
-// 4 threads share a row (or a column): thread (i, q) owns C[i][q*EPT .. q*EPT+EPT) and
-// C[q*EPT .. q*EPT+EPT)[i].  A half-iteration is: one FADD + one ex2 per element, a 4-lane shuffle
-// reduction, one __syncthreads.  Internally everything is in log2 units and the cost is shifted by
-// its minimum:  Chat = (C - c0) * log2(e)/eps,  uhat = (u - c0) * log2(e)/eps,  vhat = v * log2(e)/eps,
-// so that the exponent arguments stay O(spread/eps) instead of O(|C|/eps).
+// 4 threads share a row (or a column): thread (i, q) owns the row slice C[i][q*EPT .. q*EPT+EPT) and
+// the column slice C[q*EPT .. q*EPT+EPT)[i], both in registers.  Internal units: log2 domain, cost
+// shifted by its minimum:  Chat = (C - c0) * log2(e)/eps,  uhat = (u - c0) * log2(e)/eps,
+// vhat = v * log2(e)/eps.
+//
+// FAST PATH (stabilised scaling form).  The log-domain update
+//     uhat_i <- ahat - log2 sum_j exp2(vhat_j - Chat_ij)
+// costs one ex2 per matrix element per half-iteration and is bound by the 16 MUFU lanes of an SM.
+// With the kernel absorbed once at reference potentials,  Kt_ij = exp2(alpha_i - Chat_ij)
+// (alpha_i = row minimum, so every row holds a 1), the same update is a mat-vec:
+//     s_i = sum_j Kt_ij b_j,  b_j = exp2(vhat_j);   uhat_i = ahat + alpha_i - log2 s_i,
+//     a_i = exp2(uhat_i - alpha_i) = 2^ahat / s_i;   t_j = sum_i Kt_ij a_i,  vhat_j = ahat - log2 t_j,
+// i.e. ONE FMA per element and two MUFU ops per row.  The iterates are the same numbers (the
+// algebra is exact); only rounding differs.  The backward pass uses the same trick with the kernel
+// absorbed at the final potentials (Kt = pi): every softmax matrix of Appendix A is pi times a
+// rank-one factor.
+// SLOW PATH (guard).  If a scaling leaves [2^-90, 2^90] (ill-scaled cost / tiny eps) the forward rolls
+// back one iteration and continues, for the rest of the solve, with the plain log-domain updates with
+// max subtraction — the reference's formulation.  The backward switches to direct exponentials before
+// any rank-one factor would leave 2^+-60.
 #include "common.cuh"
 #include "sinkhorn.cuh"
 
 namespace kccot {
 
 namespace {
-constexpr float kBig = 1e30f;   // padding cost: exp2(anything - kBig) == 0, and 0 * kBig == 0
+constexpr float kBig = 1e30f;      // padding cost: exp2(anything - kBig) == 0, and 0 * kBig == 0
+constexpr float kLo = 8.0e-28f;    // ~2^-90
+constexpr float kHi = 1.2e27f;     // ~2^90
+constexpr float kExpLim = 60.f;    // |log2| allowed for a backward rank-one factor
 
 __device__ __forceinline__ float quad_sum(float v) {
   v += __shfl_xor_sync(0xffffffffu, v, 1);
@@ -25,8 +43,17 @@ __device__ __forceinline__ float quad_max(float v) {
   v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
   return v;
 }
+__device__ __forceinline__ float quad_min(float v) {
+  v = fminf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+  v = fminf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+  return v;
+}
+__device__ __forceinline__ float fast_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
-template <int NT>
 __device__ __forceinline__ float block_reduce(float v, float* red, bool is_min) {
   v = is_min ? warp_min(v) : warp_sum(v);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -52,7 +79,7 @@ __device__ __forceinline__ float load_slices(const float* __restrict__ Cn, int B
     Cc[e] = (i < B && j < B) ? Cn[(long long)j * B + i] : kBig;
     mn = fminf(mn, Cr[e]);
   }
-  const float c0 = block_reduce<0>(mn, red, true);
+  const float c0 = block_reduce(mn, red, true);
 #pragma unroll
   for (int e = 0; e < EPT; ++e) {
     Cr[e] = (Cr[e] < kBig) ? (Cr[e] - c0) * kscale : kBig;
@@ -60,191 +87,425 @@ __device__ __forceinline__ float load_slices(const float* __restrict__ Cn, int B
   }
   return c0;
 }
+
+// log-domain half update of one row (column): ahat - LSE2_e(pot[e] - Cs[e]) over the 4-thread group
+template <int EPT>
+__device__ __forceinline__ float lse_update(const float (&Cs)[EPT], const float* pot, float ahat) {
+  float t[EPT];
+  float m = -kBig;
+#pragma unroll
+  for (int e = 0; e < EPT; ++e) {
+    t[e] = (Cs[e] < kBig) ? pot[e] - Cs[e] : -kBig;      // padded entries: their potentials are unset
+    m = fmaxf(m, t[e]);
+  }
+  m = quad_max(m);
+  float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+  for (int e = 0; e < EPT; e += 2) {
+    s0 += fast_exp2(t[e] - m);
+    s1 += fast_exp2(t[e + 1] - m);
+  }
+  return ahat - (m + fast_log2(quad_sum(s0 + s1)));
+}
+
+// Vectors that every thread reads a 16-element slice of are stored PADDED: chunk q starts at
+// q*(EPT+4) floats, so the four chunk addresses of a quarter-warp fall into distinct bank groups
+// (an unpadded 64-byte chunk stride makes chunks 0/2 and 1/3 collide: 2-way conflict on every load).
+template <int EPT>
+__device__ __forceinline__ int pad_index(int j) { return (j / EPT) * (EPT + 4) + (j % EPT); }
+
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
+}
+
+// mat-vec slice: sum_e Ks[e] * vec[e] over the 4-thread group (4 independent FMA chains);
+// `saddr` = shared-window byte address of this thread's (padded) chunk
+template <int EPT>
+__device__ __forceinline__ float dot_slice(const float (&Ks)[EPT], uint32_t saddr) {
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+  for (int e = 0; e < EPT; e += 4) {
+    const float4 b = lds128(saddr + e * 4);
+    s0 = fmaf(Ks[e], b.x, s0);
+    s1 = fmaf(Ks[e + 1], b.y, s1);
+    s2 = fmaf(Ks[e + 2], b.z, s2);
+    s3 = fmaf(Ks[e + 3], b.w, s3);
+  }
+  return quad_sum((s0 + s1) + (s2 + s3));
+}
 }  // namespace
 
-template <int EPT>
+// HS = true: the potential history (L+1 rows of u and v) lives in shared memory during the solve and
+// is written to global memory once at the end; HS = false (history too large): one global store per
+// half-iteration.
+template <int EPT, bool HS>
 __global__ void __launch_bounds__(4 * 4 * EPT) sinkhorn_fwd_small_kernel(
     const float* __restrict__ C, int B, float eps, int L, int Lmin, float thresh, int exit_on_index,
     float* __restrict__ u_hist, float* __restrict__ v_hist, int32_t* __restrict__ nits_out,
     float* __restrict__ cost_out) {
   constexpr int BM = 4 * EPT;
-  __shared__ float us[BM], vs[BM], red[32];
-  __shared__ int stop_flag;
+  constexpr int BMP = 4 * (EPT + 4);
+  extern __shared__ __align__(16) float hist[];         // HS: Uh[L+1][BM] | Vh[L+1][BM]
+  __shared__ __align__(16) float us[BM], vs[BM];        // !HS: current log2-domain potentials
+  __shared__ __align__(16) float as[BMP], bs[BMP];      // linear scalings a_i, b_j of the fast path (padded)
+  __shared__ float red[32];
+  __shared__ int stop_flag, bad_flag;
   const int n = blockIdx.x;
   const int tid = threadIdx.x, i = tid >> 2, q = tid & 3;
+  const int ic = min(i, BM - 1);
+  const bool owner = (q == 0) && (i < B);
   const float kscale = kLog2e / eps;
   const float ahat = -log2f((float)B);
-  float Cr[EPT], Cc[EPT];
+  const float two_ahat = 1.f / (float)B;
+  float Cr[EPT], Cc[EPT], Kr[EPT], Kc[EPT];
   const float c0 = load_slices<EPT>(C + (long long)n * B * B, B, kscale, red, Cr, Cc);
   float* uh = u_hist + (long long)n * (L + 1) * B;
   float* vh = v_hist + (long long)n * (L + 1) * B;
-  for (int t = tid; t < BM; t += blockDim.x) { us[t] = 0.f; vs[t] = 0.f; }
-  if (tid < B) { uh[tid] = 0.f; vh[tid] = 0.f; }
-  if (tid == 0) stop_flag = 0;
+  float* Uh = hist;
+  float* Vh = hist + (HS ? (size_t)(L + 1) * BM : 0);
+  // row k of the potentials: smem history (HS) or the single current row (!HS)
+  auto urow = [&](int k) -> float* { return HS ? Uh + (size_t)k * BM : us; };
+  auto vrow = [&](int k) -> float* { return HS ? Vh + (size_t)k * BM : vs; };
+
+  // absorb the kernel at alpha_i = min_j Chat_ij, beta = 0
+  float alpha;
+  {
+    float rm = kBig;
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) rm = fminf(rm, Cr[e]);
+    alpha = quad_min(rm);
+  }
+  const int ip = pad_index<EPT>(ic);                            // padded slot of row / column i
+  const uint32_t as_q = static_cast<uint32_t>(__cvta_generic_to_shared(as)) + q * (EPT + 4) * 4;
+  const uint32_t bs_q = static_cast<uint32_t>(__cvta_generic_to_shared(bs)) + q * (EPT + 4) * 4;
+  for (int t = tid; t < BM; t += blockDim.x) { urow(0)[t] = 0.f; vrow(0)[t] = 0.f; }
+  for (int t = tid; t < BMP; t += blockDim.x) { as[t] = 0.f; bs[t] = 0.f; }
+  if (!HS && tid < B) { uh[tid] = 0.f; vh[tid] = 0.f; }
+  if (tid == 0) { stop_flag = 0; bad_flag = 0; }
+  __syncthreads();
+  if (owner) { as[ip] = alpha; bs[ip] = 1.f; }   // stage the row minima for the column slices; b = exp2(0)
+  __syncthreads();
+#pragma unroll
+  for (int e = 0; e < EPT; ++e) {
+    Kr[e] = fast_exp2(alpha - Cr[e]);                       // padded entries: exp2(x - kBig) = 0
+    Kc[e] = fast_exp2(as[q * (EPT + 4) + e] - Cc[e]);
+  }
+  __syncthreads();
+  for (int t = tid; t < BMP; t += blockDim.x) as[t] = 0.f;
   __syncthreads();
 
-  int nits = 0;
-  for (int it = 0; it < L; ++it) {
-    // ---- u update: rows ---------------------------------------------------------------------
-    float t[EPT];
-    float m = -kBig;
-#pragma unroll
-    for (int e = 0; e < EPT; ++e) {
-      t[e] = vs[q * EPT + e] - Cr[e];
-      m = fmaxf(m, t[e]);
+  const float ahat_alpha = ahat + alpha;
+  float u_cur = 0.f;            // uhat of this thread's row (all four lanes of a row hold it)
+  bool slow = false;
+  int it = 0, nits = 0;
+  for (;;) {
+    while (it < L) {
+      float du;
+      if (!slow) {
+        // ---- fast u update: s_i = sum_j Kt_ij b_j (straight-line; only the stores are predicated)
+        const float s = dot_slice<EPT>(Kr, bs_q);
+        if (bad_flag) {
+          // a scaling left the safe range during iteration it-1: roll back to the potentials before
+          // it (history row it-1) and redo it in the log domain
+          slow = true;
+          --it;
+          __syncthreads();
+          if (!HS && tid < B) { us[tid] = uh[(long long)it * B + tid]; vs[tid] = vh[(long long)it * B + tid]; }
+          __syncthreads();
+          u_cur = urow(it)[ic];
+          continue;
+        }
+        const float unew = ahat_alpha - fast_log2(s);
+        const float a = two_ahat * fast_rcp(s);
+        du = fabsf(unew - u_cur);
+        u_cur = unew;
+        if (owner) {
+          as[ip] = a;
+          urow(it + 1)[i] = unew;
+          if (!HS) uh[(long long)(it + 1) * B + i] = unew;
+          if (!(s > kLo && s < kHi)) bad_flag = 1;
+        }
+        __syncthreads();
+        // ---- fast v update: t_j = sum_i Kt_ij a_i -------------------------------------------
+        const float t = dot_slice<EPT>(Kc, as_q);
+        const float vnew = ahat - fast_log2(t);
+        const float bnew = two_ahat * fast_rcp(t);
+        if (owner) {
+          bs[ip] = bnew;
+          vrow(it + 1)[i] = vnew;
+          if (!HS) vh[(long long)(it + 1) * B + i] = vnew;
+          if (!(t > kLo && t < kHi)) bad_flag = 1;
+        }
+        __syncthreads();
+      } else {
+        // ---- log-domain updates (reference formulation) -------------------------------------
+        const float unew = lse_update<EPT>(Cr, vrow(it) + q * EPT, ahat);
+        du = fabsf(unew - u_cur);
+        u_cur = unew;
+        if (owner) {
+          urow(it + 1)[i] = unew;
+          if (!HS) uh[(long long)(it + 1) * B + i] = unew;
+        }
+        __syncthreads();
+        const float vnew = lse_update<EPT>(Cc, urow(it + 1) + q * EPT, ahat);
+        if (owner) {
+          vrow(it + 1)[i] = vnew;
+          if (!HS) vh[(long long)(it + 1) * B + i] = vnew;
+        }
+        __syncthreads();
+      }
+      nits = it + 1;
+      // ---- stopping rule (gan_utils.py:157-160 / :114-117); can only fire once the minimum count
+      // is reached, so the reduction is skipped before that -------------------------------------
+      const bool may_stop = exit_on_index ? (it >= Lmin) : (nits >= Lmin);
+      if (may_stop && nits < L && (slow || !bad_flag)) {
+        const float err = block_reduce(owner ? du : 0.f, red, false) / kscale;
+        if (tid == 0) stop_flag = (thresh > err) ? 1 : 0;
+        __syncthreads();
+        if (stop_flag) break;
+      }
+      ++it;
     }
-    m = quad_max(m);
-    float ssum = 0.f;
-#pragma unroll
-    for (int e = 0; e < EPT; ++e) ssum += fast_exp2(t[e] - m);
-    ssum = quad_sum(ssum);
-    const float unew = ahat - (m + fast_log2(ssum));
-    float du = 0.f;
-    if (q == 0 && i < B) {
-      du = fabsf(unew - us[i]);
-      us[i] = unew;
-      uh[(long long)(it + 1) * B + i] = unew;
-    }
-    __syncthreads();
-    // ---- v update: columns ------------------------------------------------------------------
-    m = -kBig;
-#pragma unroll
-    for (int e = 0; e < EPT; ++e) {
-      t[e] = us[q * EPT + e] - Cc[e];
-      m = fmaxf(m, t[e]);
-    }
-    m = quad_max(m);
-    ssum = 0.f;
-#pragma unroll
-    for (int e = 0; e < EPT; ++e) ssum += fast_exp2(t[e] - m);
-    ssum = quad_sum(ssum);
-    const float vnew = ahat - (m + fast_log2(ssum));
-    if (q == 0 && i < B) {
-      vs[i] = vnew;
-      vh[(long long)(it + 1) * B + i] = vnew;
-    }
-    __syncthreads();
-    nits = it + 1;
-    // ---- stopping rule (gan_utils.py:157-160 / :114-117); can only fire once the minimum count
-    // is reached, so the reduction is skipped before that ---------------------------------------
-    const bool may_stop = exit_on_index ? (it >= Lmin) : (nits >= Lmin);
-    if (may_stop && nits < L) {
-      const float err = block_reduce<0>(du, red, false) / kscale;
-      if (tid == 0) stop_flag = (thresh > err) ? 1 : 0;
+    // the last executed iteration may itself have tripped the guard
+    if (!slow && bad_flag && nits > 0) {
+      slow = true;
+      it = nits - 1;
       __syncthreads();
-      if (stop_flag) break;
+      if (!HS && tid < B) { us[tid] = uh[(long long)it * B + tid]; vs[tid] = vh[(long long)it * B + tid]; }
+      if (tid == 0) stop_flag = 0;
+      __syncthreads();
+      u_cur = urow(it)[ic];
+      continue;
     }
+    break;
   }
   // ---- sharp cost sum(pi * C) ---------------------------------------------------------------
   float s1 = 0.f, s0 = 0.f;
   {
-    const float ui = us[min(i, BM - 1)];
+    const float* vfin = vrow(nits) + q * EPT;
 #pragma unroll
     for (int e = 0; e < EPT; ++e) {
-      const float pi = fast_exp2(ui + vs[q * EPT + e] - Cr[e]);
+      const float pi = (Cr[e] < kBig) ? fast_exp2(u_cur + vfin[e] - Cr[e]) : 0.f;
       s0 += pi;
       s1 = fmaf(pi, Cr[e], s1);
     }
     if (i >= B) { s0 = 0.f; s1 = 0.f; }
   }
-  s1 = block_reduce<0>(s1, red, false);
-  s0 = block_reduce<0>(s0, red, false);
+  s1 = block_reduce(s1, red, false);
+  s0 = block_reduce(s0, red, false);
   if (tid == 0) {
     cost_out[n] = s1 / kscale + c0 * s0;
     nits_out[n] = nits;
   }
+  if (HS) {
+    for (int e = tid; e < (nits + 1) * B; e += blockDim.x) {
+      const int k = e / B, j = e % B;
+      uh[e] = Uh[(size_t)k * BM + j];
+      vh[e] = Vh[(size_t)k * BM + j];
+    }
+  }
 }
 
-template <int EPT>
+// HS = true: the whole potential history (nits+1 rows of u and v) is copied to shared memory up
+// front (51 KB at B=64, L=100) so every step reads its operands with LDS; HS = false (history too
+// large): two rows are staged per step with a register prefetch from L2.
+template <int EPT, bool HS>
 __global__ void __launch_bounds__(4 * 4 * EPT) sinkhorn_bwd_small_kernel(
     const float* __restrict__ C, int B, float eps, int L, const float* __restrict__ u_hist,
     const float* __restrict__ v_hist, const int32_t* __restrict__ nits_in, const float* __restrict__ gcost,
     float* __restrict__ Cbar) {
   constexpr int BM = 4 * EPT;
-  __shared__ float Us[2][BM], Vs[2][BM], ub[BM], vb[BM], red[32];
+  constexpr int PQ = EPT + 4;                           // padded chunk stride (see pad_index)
+  constexpr int BMP = 4 * PQ;
+  extern __shared__ __align__(16) float hist[];         // HS: Uh[nits+1][BMP] | Vh[nits+1][BMP]
+  __shared__ __align__(16) float Us[2][BMP], Vs[2][BMP];  // !HS: staged u^k / v^k, v^{k-1}
+  __shared__ __align__(16) float un_s[BMP], vn_s[BMP];  // final potentials (absorption reference)
+  __shared__ __align__(16) float ub[BMP], vb[BMP];      // adjoints ubar, vbar (slow-path operands)
+  __shared__ __align__(16) float ga[BMP], gb[BMP];      // fast path: factor * adjoint vectors
+  __shared__ float red[32];
+  __shared__ int slow_flag, k_slow;
   const int n = blockIdx.x;
   const int tid = threadIdx.x, i = tid >> 2, q = tid & 3;
+  const bool owner = (q == 0) && (i < B);
+  const int ip = pad_index<EPT>(min(i, BM - 1));        // padded slot of row / column i
+  const int tp = pad_index<EPT>(min(tid, BM - 1));      // padded slot of element tid (loader threads)
+  const int qo = q * PQ;                                // start of this thread's chunk
   const float kscale = kLog2e / eps;
   const float ahat = -log2f((float)B);
-  float Cr[EPT], Cc[EPT], Gr[EPT], Gc[EPT];
+  float Cr[EPT], Cc[EPT], Kr[EPT], Kc[EPT], Gr[EPT], Gc[EPT];
   load_slices<EPT>(C + (long long)n * B * B, B, kscale, red, Cr, Cc);
   const float* uh = u_hist + (long long)n * (L + 1) * B;
   const float* vh = v_hist + (long long)n * (L + 1) * B;
   const int nits = nits_in[n];
   const float g = gcost[n];
+  float* Uh = hist;
+  float* Vh = hist + (HS ? (size_t)(nits + 1) * BMP : 0);
 
-  for (int t = tid; t < 2 * BM; t += blockDim.x) { (&Us[0][0])[t] = 0.f; (&Vs[0][0])[t] = 0.f; }
-  for (int t = tid; t < BM; t += blockDim.x) { ub[t] = 0.f; vb[t] = 0.f; }
+  for (int t = tid; t < 2 * BMP; t += blockDim.x) { (&Us[0][0])[t] = 0.f; (&Vs[0][0])[t] = 0.f; }
+  for (int t = tid; t < BMP; t += blockDim.x) {
+    ub[t] = 0.f; vb[t] = 0.f; ga[t] = 0.f; gb[t] = 0.f; un_s[t] = 0.f; vn_s[t] = 0.f;
+  }
+  if (tid == 0) { slow_flag = 0; k_slow = -1; }
   __syncthreads();
   if (tid < B) {
-    Us[nits & 1][tid] = uh[(long long)nits * B + tid];
-    Vs[nits & 1][tid] = vh[(long long)nits * B + tid];
-    if (nits >= 1) Vs[(nits - 1) & 1][tid] = vh[(long long)(nits - 1) * B + tid];
+    un_s[tp] = uh[(long long)nits * B + tid];
+    vn_s[tp] = vh[(long long)nits * B + tid];
   }
   __syncthreads();
+  if (HS) {
+    // copy the history; remember the last step whose potentials are further than 2^60 from the
+    // absorption reference (steps k <= k_slow + 1 use direct exponentials)
+    for (int e = tid; e < (nits + 1) * BM; e += blockDim.x) {
+      const int k = e / BM, j = e % BM;
+      const int jp = pad_index<EPT>(j);
+      float u = 0.f, v = 0.f;
+      if (j < B) {
+        u = uh[(long long)k * B + j];
+        v = vh[(long long)k * B + j];
+        if (!(fabsf(u - un_s[jp]) <= kExpLim) || !(fabsf(v - vn_s[jp]) <= kExpLim)) atomicMax(&k_slow, k);
+      }
+      Uh[(size_t)k * BMP + jp] = u;
+      Vh[(size_t)k * BMP + jp] = v;
+    }
+  } else if (tid < B) {
+    Us[nits & 1][tp] = un_s[tp];
+    Vs[nits & 1][tp] = vn_s[tp];
+    if (nits >= 1) {
+      const float vm = vh[(long long)(nits - 1) * B + tid];
+      Vs[(nits - 1) & 1][tp] = vm;
+      if (!(fabsf(vm - vn_s[tp]) <= kExpLim)) slow_flag = 1;
+    }
+  }
+  __syncthreads();
+  const float un_i = un_s[ip], vn_i = vn_s[ip];    // row i / column i of this thread
   // ---- adjoint seeds.  cost = sum(pi*C) = sum(pi*(C - c0)) + c0*sum(pi), and sum(pi) == 1 identically
   // in the inputs (the last v-update normalises every column of pi to 1/B), so the c0 term has zero
   // gradient: seed with C' = C - c0.  Cbar = pi (1 - C'/eps), ubar = rowsum(pi C')/eps, vbar =
   // colsum(pi C')/eps.  This removes the O(|C|/eps) cancellation the reference's fp32 gradient suffers.
   {
-    const float* U = Us[nits & 1];
-    const float* V = Vs[nits & 1];
-    const float ui = U[min(i, BM - 1)], vi = V[min(i, BM - 1)];
     float ru = 0.f, rv = 0.f;
 #pragma unroll
     for (int e = 0; e < EPT; ++e) {
-      const float ce_r = Cr[e] * kLn2;                       // (C - c0) / eps (row slice)
-      const float pr = fast_exp2(ui + V[q * EPT + e] - Cr[e]);
-      Gr[e] = pr * (1.f - ce_r);
-      ru = fmaf(pr, ce_r, ru);
+      const float ce_r = Cr[e] * kLn2;                              // (C - c0) / eps (row slice)
+      Kr[e] = fast_exp2(un_i + vn_s[qo + e] - Cr[e]);               // pi, row slice
+      Gr[e] = Kr[e] * (1.f - ce_r);
+      ru = fmaf(Kr[e], ce_r, ru);
       const float ce_c = Cc[e] * kLn2;
-      const float pc = fast_exp2(U[q * EPT + e] + vi - Cc[e]);
-      rv = fmaf(pc, ce_c, rv);
+      Kc[e] = fast_exp2(un_s[qo + e] + vn_i - Cc[e]);               // pi, column slice
+      rv = fmaf(Kc[e], ce_c, rv);
       Gc[e] = 0.f;
     }
     ru = quad_sum(ru);
     rv = quad_sum(rv);
-    if (q == 0 && i < B) { ub[i] = ru; vb[i] = rv; }
+    if (owner) {
+      ub[ip] = ru;
+      vb[ip] = rv;
+      gb[ip] = (float)B * rv;          // exp2(v^n_j - v^n_j - ahat) * vbar_j
+    }
   }
   __syncthreads();
+  const uint32_t ga_q = static_cast<uint32_t>(__cvta_generic_to_shared(ga)) + qo * 4;
+  const uint32_t gb_q = static_cast<uint32_t>(__cvta_generic_to_shared(gb)) + qo * 4;
+  const int kslow = HS ? k_slow : -1;
 
+  bool slow = false;
   for (int k = nits; k >= 1; --k) {
     const int b = k & 1;
-    // prefetch the next step's potentials (L2) while this step computes
+    const float* Uk = HS ? Uh + (size_t)k * BMP : Us[b];
+    const float* Vk = HS ? Vh + (size_t)k * BMP : Vs[b];
+    const float* Vkm1 = HS ? Vh + (size_t)(k - 1) * BMP : Vs[b ^ 1];
+    // !HS: prefetch the next step's potentials (L2) while this step computes
     float pu = 0.f, pv = 0.f;
-    if (tid < B && k >= 2) {
+    if (!HS && tid < B && k >= 2) {
       pu = uh[(long long)(k - 1) * B + tid];
       pv = vh[(long long)(k - 2) * B + tid];
     }
+    if (HS) slow = (k <= kslow + 1);
+    else if (!slow) slow = (slow_flag != 0);
     // ---- through v^k = a - eps*LSE_i((u^k_i - C_ij)/eps):  Pv_ij = exp((u^k_i + v^k_j - a - C_ij)/eps)
+    //      Cbar += Pv * vbar_j ;  ubar_i = (k == nits ? ubar_i : 0) - sum_j Pv_ij vbar_j
     {
-      const float ui = Us[b][min(i, BM - 1)] - ahat;
-      float acc = 0.f;
+      const float uk_i = Uk[ip];
+      float part;
+      if (!slow) {
+        // Pv_ij vbar_j = pi_ij * exp2(u^k_i - u^n_i) * gb_j
+        const float fa = fast_exp2(uk_i - un_i);
+        float a0 = 0.f, a1 = 0.f;
 #pragma unroll
-      for (int e = 0; e < EPT; ++e) {
-        const float w = fast_exp2(ui + Vs[b][q * EPT + e] - Cr[e]) * vb[q * EPT + e];
-        Gr[e] += w;
-        acc += w;
+        for (int e = 0; e < EPT; e += 4) {
+          const float4 w = lds128(gb_q + e * 4);
+          const float t0 = Kr[e] * w.x, t1 = Kr[e + 1] * w.y, t2 = Kr[e + 2] * w.z, t3 = Kr[e + 3] * w.w;
+          Gr[e] = fmaf(t0, fa, Gr[e]);
+          Gr[e + 1] = fmaf(t1, fa, Gr[e + 1]);
+          Gr[e + 2] = fmaf(t2, fa, Gr[e + 2]);
+          Gr[e + 3] = fmaf(t3, fa, Gr[e + 3]);
+          a0 += t0 + t2;
+          a1 += t1 + t3;
+        }
+        part = (a0 + a1) * fa;
+      } else {
+        const float ui = uk_i - ahat;
+        float a0 = 0.f;
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) {
+          const float w = fast_exp2(ui + Vk[qo + e] - Cr[e]) * vb[qo + e];
+          Gr[e] += w;
+          a0 += w;
+        }
+        part = a0;
       }
-      acc = quad_sum(acc);
-      if (q == 0 && i < B) ub[i] = ((k == nits) ? ub[i] : 0.f) - acc;
+      const float acc = quad_sum(part);
+      if (owner) {
+        const float ubn = ((k == nits) ? ub[ip] : 0.f) - acc;
+        ub[ip] = ubn;
+        ga[ip] = fast_exp2(fminf(fmaxf(uk_i - un_i, -kExpLim), kExpLim)) * ubn;   // for the column phase
+      }
     }
     __syncthreads();
+    if (!HS && !slow) slow = (slow_flag != 0);
     // ---- through u^k = a - eps*LSE_j((v^{k-1}_j - C_ij)/eps):  Pu_ij = exp((u^k_i + v^{k-1}_j - a - C_ij)/eps)
+    //      Cbar += Pu * ubar_i ;  vbar_j = - sum_i Pu_ij ubar_i
     {
-      const float vj = Vs[b ^ 1][min(i, BM - 1)] - ahat;
-      float acc = 0.f;
+      const float vkm1_j = Vkm1[ip];
+      const float fb = fast_exp2(fminf(fmaxf(vkm1_j - vn_i, -kExpLim), kExpLim) - ahat);
+      float part;
+      if (!slow) {
+        float a0 = 0.f, a1 = 0.f;
 #pragma unroll
-      for (int e = 0; e < EPT; ++e) {
-        const float w = fast_exp2(Us[b][q * EPT + e] + vj - Cc[e]) * ub[q * EPT + e];
-        Gc[e] += w;
-        acc += w;
+        for (int e = 0; e < EPT; e += 4) {
+          const float4 w = lds128(ga_q + e * 4);
+          const float t0 = Kc[e] * w.x, t1 = Kc[e + 1] * w.y, t2 = Kc[e + 2] * w.z, t3 = Kc[e + 3] * w.w;
+          Gc[e] = fmaf(t0, fb, Gc[e]);
+          Gc[e + 1] = fmaf(t1, fb, Gc[e + 1]);
+          Gc[e + 2] = fmaf(t2, fb, Gc[e + 2]);
+          Gc[e + 3] = fmaf(t3, fb, Gc[e + 3]);
+          a0 += t0 + t2;
+          a1 += t1 + t3;
+        }
+        part = (a0 + a1) * fb;
+      } else {
+        const float vj = vkm1_j - ahat;
+        float a0 = 0.f;
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) {
+          const float w = fast_exp2(Uk[qo + e] + vj - Cc[e]) * ub[qo + e];
+          Gc[e] += w;
+          a0 += w;
+        }
+        part = a0;
       }
-      acc = quad_sum(acc);
-      if (q == 0 && i < B) vb[i] = -acc;
-      if (tid < B && k >= 2) {
-        Us[b ^ 1][tid] = pu;     // u^{k-1}
-        Vs[b][tid] = pv;         // v^{k-2}   (v^k is dead after the row phase above)
+      const float acc = quad_sum(part);
+      if (owner) {
+        vb[ip] = -acc;
+        gb[ip] = fb * (-acc);          // factor of the next row phase: v^{k-1} here is its v^k
+      }
+      if (!HS && tid < B && k >= 2) {
+        Us[b ^ 1][tp] = pu;     // u^{k-1}
+        Vs[b][tp] = pv;         // v^{k-2}   (v^k is dead after the row phase above)
+        // a potential further than 2^60 from the reference: direct exponentials from the next step on
+        if (!(fabsf(pu - un_s[tp]) <= kExpLim) || !(fabsf(pv - vn_s[tp]) <= kExpLim)) slow_flag = 1;
       }
     }
     __syncthreads();
@@ -268,16 +529,51 @@ __global__ void __launch_bounds__(4 * 4 * EPT) sinkhorn_bwd_small_kernel(
   }
 }
 
+template <int EPT>
+static int launch_fwd_t(const float* C, int nsolve, int B, float eps, int L, int Lmin, float thresh, int exit_on_index,
+                        float* u_hist, float* v_hist, int32_t* nits, float* cost, int threads, cudaStream_t st) {
+  const size_t hist_bytes = (size_t)2 * (L + 1) * 4 * EPT * sizeof(float);
+  if (hist_bytes <= 160 * 1024) {
+    static bool attr = false;
+    if (!attr) {
+      KCCOT_CUDA(cudaFuncSetAttribute(sinkhorn_fwd_small_kernel<EPT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)(160 * 1024)));
+      attr = true;
+    }
+    sinkhorn_fwd_small_kernel<EPT, true><<<nsolve, threads, hist_bytes, st>>>(C, B, eps, L, Lmin, thresh, exit_on_index,
+                                                                          u_hist, v_hist, nits, cost);
+  } else {
+    sinkhorn_fwd_small_kernel<EPT, false><<<nsolve, threads, 0, st>>>(C, B, eps, L, Lmin, thresh, exit_on_index, u_hist,
+                                                                    v_hist, nits, cost);
+  }
+  KCCOT_LAUNCH_CHECK();
+  return KCCOT_OK;
+}
+
 int launch_sinkhorn_fwd_small(const float* C, int nsolve, int B, float eps, int L, int Lmin, float thresh,
                               int exit_on_index, float* u_hist, float* v_hist, int32_t* nits, float* cost,
                               cudaStream_t st) {
   const int threads = ((4 * B + 31) / 32) * 32;
   if (B <= 32)
-    sinkhorn_fwd_small_kernel<8><<<nsolve, threads, 0, st>>>(C, B, eps, L, Lmin, thresh, exit_on_index, u_hist,
-                                                             v_hist, nits, cost);
-  else
-    sinkhorn_fwd_small_kernel<16><<<nsolve, threads, 0, st>>>(C, B, eps, L, Lmin, thresh, exit_on_index, u_hist,
-                                                              v_hist, nits, cost);
+    return launch_fwd_t<8>(C, nsolve, B, eps, L, Lmin, thresh, exit_on_index, u_hist, v_hist, nits, cost, threads, st);
+  return launch_fwd_t<16>(C, nsolve, B, eps, L, Lmin, thresh, exit_on_index, u_hist, v_hist, nits, cost, threads, st);
+}
+
+template <int EPT>
+static int launch_bwd_t(const float* C, int nsolve, int B, float eps, int L, const float* u_hist, const float* v_hist,
+                        const int32_t* nits, const float* gcost, float* Cbar, int threads, cudaStream_t st) {
+  const size_t hist_bytes = (size_t)2 * (L + 1) * 4 * (EPT + 4) * sizeof(float);
+  if (hist_bytes <= 160 * 1024) {
+    static size_t attr = 0;
+    if (hist_bytes > attr) {
+      KCCOT_CUDA(cudaFuncSetAttribute(sinkhorn_bwd_small_kernel<EPT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)(160 * 1024)));
+      attr = 160 * 1024;
+    }
+    sinkhorn_bwd_small_kernel<EPT, true><<<nsolve, threads, hist_bytes, st>>>(C, B, eps, L, u_hist, v_hist, nits, gcost, Cbar);
+  } else {
+    sinkhorn_bwd_small_kernel<EPT, false><<<nsolve, threads, 0, st>>>(C, B, eps, L, u_hist, v_hist, nits, gcost, Cbar);
+  }
   KCCOT_LAUNCH_CHECK();
   return KCCOT_OK;
 }
@@ -286,12 +582,8 @@ int launch_sinkhorn_bwd_small(const float* C, int nsolve, int B, float eps, int 
                               const float* v_hist, const int32_t* nits, const float* gcost, float* Cbar,
                               cudaStream_t st) {
   const int threads = ((4 * B + 31) / 32) * 32;
-  if (B <= 32)
-    sinkhorn_bwd_small_kernel<8><<<nsolve, threads, 0, st>>>(C, B, eps, L, u_hist, v_hist, nits, gcost, Cbar);
-  else
-    sinkhorn_bwd_small_kernel<16><<<nsolve, threads, 0, st>>>(C, B, eps, L, u_hist, v_hist, nits, gcost, Cbar);
-  KCCOT_LAUNCH_CHECK();
-  return KCCOT_OK;
+  if (B <= 32) return launch_bwd_t<8>(C, nsolve, B, eps, L, u_hist, v_hist, nits, gcost, Cbar, threads, st);
+  return launch_bwd_t<16>(C, nsolve, B, eps, L, u_hist, v_hist, nits, gcost, Cbar, threads, st);
 }
 
 }  // namespace kccot

@@ -153,11 +153,19 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
                : "memory");
 }
 
-// round-to-nearest fp32 -> tf32 (low 13 mantissa bits zero)
+// round-to-nearest (ties away) fp32 -> tf32: low 13 mantissa bits zero.  Two integer ops; cvt.rna.tf32.f32
+// expands to ~6 instructions on sm_100a because it also handles Inf/NaN, which video data never holds.
 __device__ __forceinline__ float to_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+}
+
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t saddr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
@@ -169,6 +177,6 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 // host: encode a 3-D fp32 tensor map [d2][d1][d0] with a (b0, b1, 1) box; atom32 = false: 128-byte swizzle
 // with 16-byte atoms (K-major operands), true: 128-byte swizzle with 32-byte atoms (MN-major tf32 operands)
 int encode_tmap_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
-                   uint64_t stride2_bytes, uint32_t b0, uint32_t b1, bool atom32 = false);
+                   uint64_t stride2_bytes, uint32_t b0, uint32_t b1, bool atom32 = false, bool noswizzle = false);
 
 }  // namespace kccot

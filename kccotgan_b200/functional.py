@@ -175,10 +175,22 @@ class SinkhornFn(torch.autograd.Function):
 # ------------------------------------------------------------------------------------------------
 # fused mixed loss: 2*S(real,fake) - S(real,real) - S(fake,fake), one pass over the videos
 # ------------------------------------------------------------------------------------------------
+_SIZES = {}
+
+
+def _mixed_sizes(B, K, L):
+    key = (B, K, L)
+    if key not in _SIZES:
+        lib = _lib.load()
+        _SIZES[key] = (int(lib.kccot_mixed_loss_saved_bytes(1, B, L)), int(lib.kccot_mixed_loss_workspace_bytes(1, B, K, L)))
+    return _SIZES[key]
+
+
 class MixedLossFn(torch.autograd.Function):
+    """One C-ABI call per direction (kccot_mixed_loss_fwd / _bwd)."""
+
     @staticmethod
     def forward(ctx, real, fake, h_fake, m_real, h_real, m_fake, s, eps, L):
-        nprob = 1
         R, F = _flat_rows(real, "f_real"), _flat_rows(fake, "f_fake")
         if R.shape != F.shape:
             raise ValueError(f"f_real and f_fake must have the same shape, got {tuple(real.shape)} vs "
@@ -190,54 +202,48 @@ class MixedLossFn(torch.autograd.Function):
         for t, n in zip(hs, ("h_fake", "m_real", "h_real", "m_fake")):
             if tuple(t.shape) != (B, T, J):
                 raise ValueError(f"{n}: expected shape {(B, T, J)}, got {tuple(t.shape)}")
+        if T < 2:
+            raise ValueError(f"the martingale term needs at least 2 time steps, got T={T}")
         dev = R.device
-        lib = _lib.load()
-        C3 = torch.empty((nprob * 3, B, B), dtype=torch.float32, device=dev)
-        ws = _ws(lib.kccot_mixed_cost_workspace_bytes(nprob, B, K), dev)
         L = int(L)
-        uh = torch.empty((3 * nprob, L + 1, B), dtype=torch.float32, device=dev)
-        vh = torch.empty_like(uh)
-        nits = torch.empty((3 * nprob,), dtype=torch.int32, device=dev)
-        cost = torch.empty((3 * nprob,), dtype=torch.float32, device=dev)
-        ws2 = _ws(lib.kccot_sinkhorn_workspace_bytes(3 * nprob, B, L), dev)
+        saved_bytes, ws_bytes = _mixed_sizes(B, K, L)
+        saved = torch.empty(saved_bytes, dtype=torch.uint8, device=dev)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        out = torch.empty(4, dtype=torch.float32, device=dev)          # loss | xy, xx, yy
         with torch.cuda.device(dev):
-            st = _stream(dev)
-            _lib.call("kccot_mixed_cost_fwd", _ptr(R), _ptr(F), nprob, B, K, _ptr(hs[0]), _ptr(hs[1]), _ptr(hs[2]),
-                      _ptr(hs[3]), T, J, float(s), _ptr(C3), _ptr(ws), ws.numel(), _PATH["flags"], st)
-            _lib.call("kccot_sinkhorn_fwd", _ptr(C3), 3 * nprob, B, float(eps), L, 100, 1e-2, 0, _ptr(uh), _ptr(vh),
-                      _ptr(nits), _ptr(cost), _ptr(ws2), ws2.numel(), st)
-        ctx.save_for_backward(R, F, *hs, C3, uh, vh, nits)
+            _lib.call("kccot_mixed_loss_fwd", _ptr(R), _ptr(F), 1, B, K, _ptr(hs[0]), _ptr(hs[1]), _ptr(hs[2]),
+                      _ptr(hs[3]), T, J, float(s), float(eps), L, _ptr(saved), ctypes.c_void_p(out.data_ptr()),
+                      ctypes.c_void_p(out.data_ptr() + 4), _ptr(ws), ws_bytes, _PATH["flags"], _stream(dev))
+        ctx.save_for_backward(R, F, *hs, saved)
         ctx.meta = (real.shape, fake.shape, float(s), float(eps), L)
-        loss = 2.0 * cost[0] - cost[1] - cost[2]
-        ctx.mark_non_differentiable(cost)
-        return loss, cost
+        loss, terms = out[0], out[1:]
+        ctx.mark_non_differentiable(terms)
+        return loss, terms
 
     @staticmethod
-    def backward(ctx, gloss, _gcost):
-        R, F, h_fake, m_real, h_real, m_fake, C3, uh, vh, nits = ctx.saved_tensors
+    def backward(ctx, gloss, _gterms):
+        R, F, h_fake, m_real, h_real, m_fake, saved = ctx.saved_tensors
         rshape, fshape, s, eps, L = ctx.meta
         B, K = R.shape
         T, J = h_fake.shape[1], h_fake.shape[2]
         dev = R.device
-        lib = _lib.load()
         need = ctx.needs_input_grad
-        gcost = gloss.reshape(1).float() * torch.tensor([2.0, -1.0, -1.0], dtype=torch.float32, device=dev)
-        Cbar3 = torch.empty_like(C3)
-        ws2 = _ws(lib.kccot_sinkhorn_workspace_bytes(3, B, L), dev)
+        gloss = gloss.reshape(1)
+        if gloss.dtype != torch.float32 or not gloss.is_contiguous():
+            gloss = gloss.float().contiguous()
         g_real = torch.empty_like(R) if need[0] else None
         g_fake = torch.empty_like(F) if need[1] else None
         gh_fake = torch.empty_like(h_fake) if need[2] else None
         gm_real = torch.empty_like(m_real) if need[3] else None
         gh_real = torch.empty_like(h_real) if need[4] else None
         gm_fake = torch.empty_like(m_fake) if need[5] else None
-        ws = _ws(lib.kccot_mixed_cost_bwd_workspace_bytes(1, B, K), dev)
+        _, ws_bytes = _mixed_sizes(B, K, L)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
-            st = _stream(dev)
-            _lib.call("kccot_sinkhorn_bwd", _ptr(C3), 3, B, eps, L, _ptr(uh), _ptr(vh), _ptr(nits), _ptr(gcost),
-                      _ptr(Cbar3), _ptr(ws2), ws2.numel(), st)
-            _lib.call("kccot_mixed_cost_bwd", _ptr(Cbar3), _ptr(R), _ptr(F), 1, B, K, _ptr(h_fake), _ptr(m_real),
-                      _ptr(h_real), _ptr(m_fake), T, J, s, _ptr(g_real), _ptr(g_fake), _ptr(gh_fake), _ptr(gm_real),
-                      _ptr(gh_real), _ptr(gm_fake), _ptr(ws), ws.numel(), _PATH["flags"], st)
+            _lib.call("kccot_mixed_loss_bwd", _ptr(gloss), _ptr(R), _ptr(F), 1, B, K, _ptr(h_fake), _ptr(m_real),
+                      _ptr(h_real), _ptr(m_fake), T, J, s, eps, L, _ptr(saved), _ptr(g_real), _ptr(g_fake),
+                      _ptr(gh_fake), _ptr(gm_real), _ptr(gh_real), _ptr(gm_fake), _ptr(ws), ws_bytes, _PATH["flags"],
+                      _stream(dev))
         g_real = g_real.reshape(rshape) if g_real is not None else None
         g_fake = g_fake.reshape(fshape) if g_fake is not None else None
         return g_real, g_fake, gh_fake, gm_real, gh_real, gm_fake, None, None, None

@@ -201,7 +201,7 @@ def test_mixed_loss_full_size(gu, name, kind, path):
 # Sinkhorn kernels in isolation against the fp64 oracle on the same (fp32-rounded) cost
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("B,eps,L", [(64, 1.0, 100), (32, 0.8, 100), (17, 0.3, 40), (64, 1.0, 250), (96, 1.0, 60),
-                                     (200, 0.7, 30), (96, 2.0, 300)])
+                                     (200, 0.7, 30), (96, 2.0, 300), (64, 1.0, 600), (8, 0.5, 100)])
 def test_sinkhorn_kernels_vs_oracle(B, eps, L):
     from kccotgan_b200.functional import SinkhornFn
     from oracle import closed_form as cf
@@ -220,6 +220,29 @@ def test_sinkhorn_kernels_vs_oracle(B, eps, L):
         e = rel_l2(gC[n].cpu().numpy(), Cb)
         print(B, eps, L, n, "nits", rn, "cost rel", abs(float(cost[n]) - ref) / abs(ref), "Cbar rel-L2", e)
         assert e < GRAD_TOL
+
+
+@pytest.mark.parametrize("B,eps,L", [(24, 0.02, 30), (64, 0.05, 120), (40, 0.01, 10)])
+def test_sinkhorn_guard_path(B, eps, L):
+    """Ill-scaled problems (spread/eps in the hundreds) leave the fp32 range of the scaling form: the
+    kernels must roll back to the log-domain updates and still match the oracle."""
+    from kccotgan_b200.functional import SinkhornFn
+    from oracle import closed_form as cf
+    rng = np.random.default_rng(B + L)
+    C = (900.0 + 4.0 * rng.standard_normal((2, B, B))).astype(np.float32)
+    C[1] = np.abs(C[1] - 900.0) * 3.0
+    Ct = torch.from_numpy(C).cuda().requires_grad_(True)
+    cost, nits = SinkhornFn.apply(Ct, eps, L, 100, 1e-2, False)
+    gC, = torch.autograd.grad(cost.sum(), Ct)
+    assert torch.isfinite(cost).all() and torch.isfinite(gC).all()
+    for n in range(2):
+        ref, uh, vh, rn = cf.sinkhorn_forward(C[n].astype(np.float64), eps, L, Lmin=100, thresh=1e-2)
+        Cb = cf.sinkhorn_backward(C[n].astype(np.float64), eps, uh, vh, rn)
+        e = rel_l2(gC[n].cpu().numpy(), Cb)
+        print("guard", B, eps, L, n, "nits", int(nits[n]), rn, "cost rel", abs(float(cost[n]) - ref) / abs(ref), "Cbar", e)
+        assert int(nits[n]) == rn
+        assert abs(float(cost[n]) - ref) <= LOSS_TOL * abs(ref)
+        assert e < 2e-3          # eps this small makes the plan a near-permutation: ill-conditioned gradient
 
 
 # ---------------------------------------------------------------------------------------------
