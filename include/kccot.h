@@ -117,6 +117,28 @@ int kccot_sinkhorn_bwd(const float* C, int nsolve, int B, float eps, int L, cons
                        void* ws, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Row-sharded single problem (BASELINE config 5).  This rank owns rows
+ * [row0, row0+Brows) of the B x B cost (Crows [Brows,B]).  The u-update is local; the v-update needs a
+ * column log-sum-exp over all rows: each rank produces colstat [2,B] = (max, sum exp2(. - max)) over its
+ * rows, the CALLER all-gathers them (NCCL over NVLink) and every rank combines.  The reverse pass
+ * exchanges plain [B] sums.  Potentials are in the library's internal log2 units; `ws` (same buffer for
+ * all calls of one solve) starts with the cost shift: the caller all-reduces (MIN) the float at ws+0
+ * after kccot_shard_begin.  One kernel boundary per half-iteration pair is the synchronisation point.
+ * ------------------------------------------------------------------------------------------ */
+size_t kccot_shard_workspace_bytes(int Brows, int B);
+int kccot_shard_begin(const float* Crows, int Brows, int B, void* ws, size_t ws_bytes, void* stream);
+int kccot_shard_fwd_rows(const float* Crows, int Brows, int B, float eps, const float* v, float* u_rows,
+                         float* colstat, void* ws, size_t ws_bytes, void* stream);
+int kccot_shard_fwd_combine(const float* colstat_all, int nranks, int B, float* v, void* ws, void* stream);
+int kccot_shard_cost_partial(const float* Crows, int Brows, int B, float eps, const float* u_rows,
+                             const float* v, float* partial, void* ws, void* stream);
+int kccot_shard_bwd_seed(const float* Crows, int Brows, int B, float eps, const float* u_rows, const float* v,
+                         float g, float* Cbar_rows, float* ubar_rows, float* colsum, void* ws, void* stream);
+int kccot_shard_bwd_rows(const float* Crows, int Brows, int B, float eps, const float* u_k_rows,
+                         const float* v_k, const float* v_km1, const float* vbar, int first,
+                         float* ubar_rows, float* Cbar_rows, float* colsum, void* ws, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Fused mixed Sinkhorn loss — gan_utils.py:204-227 (compute_sinkhorn_loss) in ONE call per direction:
  *   fwd: stacked squared distances -> three cost matrices -> three Sinkhorn solves -> 2*xy - xx - yy
  *   bwd: three reverse solves -> adjoint GEMMs -> gradients of real / fake / h_fake / m_real / h_real / m_fake

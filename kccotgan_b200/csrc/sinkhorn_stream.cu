@@ -94,17 +94,41 @@ __global__ void __launch_bounds__(NT) stream_fwd_combine_kernel(const float* __r
                                                                 const float* __restrict__ colsum_part, int nparts,
                                                                 int B, float ahat, float* __restrict__ v_cur,
                                                                 float* __restrict__ v_hist_row,
-                                                                const StreamState* state) {
+                                                                const StreamState* state, long long pstride) {
   if (state->done) return;
+  const int j = blockIdx.x * NT + threadIdx.x;
+  if (j >= B) return;
+  float M = kNegBig;
+  for (int p = 0; p < nparts; ++p) M = fmaxf(M, colmax_part[p * pstride + j]);
+  float S = 0.f;
+  for (int p = 0; p < nparts; ++p) S += colsum_part[p * pstride + j] * fast_exp2(colmax_part[p * pstride + j] - M);
+  const float v = ahat - (M + fast_log2(S));
+  v_cur[j] = v;
+  if (v_hist_row) v_hist_row[j] = v;
+}
+
+// reduce this rank's per-chunk (max, sumexp) partials to one pair per column (what the ranks exchange)
+__global__ void __launch_bounds__(NT) stream_colstat_reduce_kernel(const float* __restrict__ colmax_part,
+                                                                   const float* __restrict__ colsum_part, int nparts,
+                                                                   int B, float* __restrict__ out_max,
+                                                                   float* __restrict__ out_sum) {
   const int j = blockIdx.x * NT + threadIdx.x;
   if (j >= B) return;
   float M = kNegBig;
   for (int p = 0; p < nparts; ++p) M = fmaxf(M, colmax_part[(long long)p * B + j]);
   float S = 0.f;
   for (int p = 0; p < nparts; ++p) S += colsum_part[(long long)p * B + j] * fast_exp2(colmax_part[(long long)p * B + j] - M);
-  const float v = ahat - (M + fast_log2(S));
-  v_cur[j] = v;
-  if (v_hist_row) v_hist_row[j] = v;
+  out_max[j] = M;
+  out_sum[j] = S;
+}
+
+__global__ void __launch_bounds__(NT) stream_colsum_reduce_kernel(const float* __restrict__ part, int nparts, int B,
+                                                                  float* __restrict__ out) {
+  const int j = blockIdx.x * NT + threadIdx.x;
+  if (j >= B) return;
+  float acc = 0.f;
+  for (int p = 0; p < nparts; ++p) acc += part[(long long)p * B + j];
+  out[j] = acc;
 }
 
 __global__ void stream_stop_kernel(StreamState* state, int iter_1based, float thresh, float kscale, int cond_ok) {
@@ -189,24 +213,15 @@ __global__ void __launch_bounds__(NT) stream_bwd_seed_kernel(const float* __rest
   }
 }
 
-// reverse step k:  rows: Pv -> Cbar += Pv*vbar_j, ubar_i = (k==nits ? ubar_i : 0) - sum_j Pv vbar_j
+// reverse step k:  rows: Pv -> Cbar += Pv*vbar_j, ubar_i = (first ? ubar_i : 0) - sum_j Pv vbar_j
 //                  cols: Pu -> Cbar += Pu*ubar_i, partial of sum_i Pu ubar_i
-__global__ void __launch_bounds__(NT) stream_bwd_rows_kernel(const float* __restrict__ C, int Brows, int row_off, int B,
-                                                             float kscale, float ahat,
-                                                             const float* __restrict__ u_hist,
-                                                             const float* __restrict__ v_hist,
-                                                             const int32_t* __restrict__ nits_p, int k,
-                                                             const float* __restrict__ shift_p,
-                                                             const float* __restrict__ vbar, float* __restrict__ ubar,
-                                                             float* __restrict__ Cbar,
-                                                             float* __restrict__ colsum_part) {
-  const int nits = *nits_p;
-  if (k > nits) return;
-  const float shift = *shift_p;
+__device__ __forceinline__ void stream_bwd_rows_core(const float* __restrict__ C, int Brows, int B, float kscale,
+                                                     float ahat, const float* __restrict__ uk,
+                                                     const float* __restrict__ vk, const float* __restrict__ vkm1,
+                                                     bool first, float shift, const float* __restrict__ vbar,
+                                                     float* __restrict__ ubar, float* __restrict__ Cbar,
+                                                     float* __restrict__ colsum_part) {
   __shared__ float us[RC], ubs[RC];
-  const float* uk = u_hist + (long long)k * B + row_off;
-  const float* vk = v_hist + (long long)k * B;
-  const float* vkm1 = v_hist + (long long)(k - 1) * B;
   const int r0 = blockIdx.x * RC;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int rr = warp; rr < RC; rr += NT / 32) {
@@ -223,7 +238,7 @@ __global__ void __launch_bounds__(NT) stream_bwd_rows_kernel(const float* __rest
     }
     acc = warp_sum(acc);
     if (lane == 0) {
-      const float ub = ((k == nits) ? ubar[r] : 0.f) - acc;
+      const float ub = (first ? ubar[r] : 0.f) - acc;
       ubar[r] = ub;
       us[rr] = ui;
       ubs[rr] = ub;
@@ -242,6 +257,35 @@ __global__ void __launch_bounds__(NT) stream_bwd_rows_kernel(const float* __rest
     }
     colsum_part[(long long)blockIdx.x * B + j] = acc;
   }
+}
+
+// single-GPU form: operands located in the saved history by the device-side iteration count
+__global__ void __launch_bounds__(NT) stream_bwd_rows_kernel(const float* __restrict__ C, int Brows, int row_off, int B,
+                                                             float kscale, float ahat,
+                                                             const float* __restrict__ u_hist,
+                                                             const float* __restrict__ v_hist,
+                                                             const int32_t* __restrict__ nits_p, int k,
+                                                             const float* __restrict__ shift_p,
+                                                             const float* __restrict__ vbar, float* __restrict__ ubar,
+                                                             float* __restrict__ Cbar,
+                                                             float* __restrict__ colsum_part) {
+  const int nits = *nits_p;
+  if (k > nits) return;
+  stream_bwd_rows_core(C, Brows, B, kscale, ahat, u_hist + (long long)k * B + row_off, v_hist + (long long)k * B,
+                       v_hist + (long long)(k - 1) * B, k == nits, *shift_p, vbar, ubar, Cbar, colsum_part);
+}
+
+// sharded form: the three potential vectors are passed directly
+__global__ void __launch_bounds__(NT) stream_bwd_rows_direct_kernel(const float* __restrict__ C, int Brows, int B,
+                                                                    float kscale, float ahat,
+                                                                    const float* __restrict__ uk,
+                                                                    const float* __restrict__ vk,
+                                                                    const float* __restrict__ vkm1, int first,
+                                                                    const float* __restrict__ shift_p,
+                                                                    const float* __restrict__ vbar,
+                                                                    float* __restrict__ ubar, float* __restrict__ Cbar,
+                                                                    float* __restrict__ colsum_part) {
+  stream_bwd_rows_core(C, Brows, B, kscale, ahat, uk, vk, vkm1, first != 0, *shift_p, vbar, ubar, Cbar, colsum_part);
 }
 
 __global__ void __launch_bounds__(NT) stream_bwd_combine_kernel(const float* __restrict__ colsum_part, int nparts, int B,
@@ -299,7 +343,7 @@ int stream_sinkhorn_fwd(const float* C, int B, float eps, int L, int Lmin, float
                                                     w.part_a, w.part_b, w.state, may_stop ? 1 : 0);
     KCCOT_LAUNCH_CHECK();
     stream_fwd_combine_kernel<<<cgrid, NT, 0, st>>>(w.part_a, w.part_b, w.nchunk, B, ahat, w.v_cur,
-                                                    v_hist + (long long)(it + 1) * B, w.state);
+                                                    v_hist + (long long)(it + 1) * B, w.state, (long long)B);
     KCCOT_LAUNCH_CHECK();
     if (may_stop) {
       stream_stop_kernel<<<1, 1, 0, st>>>(w.state, it + 1, thresh, kscale, 1);
@@ -340,3 +384,109 @@ int stream_sinkhorn_bwd(const float* C, int B, float eps, int L, const float* u_
 }
 
 }  // namespace kccot
+
+// ------------------------------------------------------------------------------------------------
+// Row-sharded single problem (BASELINE config 5): this rank owns rows [row0, row0 + Brows) of the
+// B x B cost.  One call per half-iteration pair; the caller exchanges the [B] column statistics
+// between ranks (NCCL all-gather / all-reduce over NVLink) between the calls.  kccotgan_b200/sharded.py.
+// ------------------------------------------------------------------------------------------------
+using namespace kccot;
+
+extern "C" {
+
+size_t kccot_shard_workspace_bytes(int Brows, int B) { return stream_workspace_bytes(Brows, B); }
+
+// state (in ws): float shift at byte 0 = min over this rank's rows; the caller all-reduces (MIN) that float
+int kccot_shard_begin(const float* Crows, int Brows, int B, void* ws, size_t ws_bytes, void* stream) {
+  KCCOT_CHECK_ARG(Crows && ws && Brows >= 1 && B >= 1 && ws_bytes >= stream_workspace_bytes(Brows, B), "bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  StreamWs w = carve(ws, Brows, B);
+  stream_state_init_kernel<<<1, 1, 0, st>>>(w.state);
+  KCCOT_LAUNCH_CHECK();
+  const long long n = (long long)Brows * B;
+  stream_min_kernel<<<(int)min((long long)4 * num_sms(), (n + NT - 1) / NT), NT, 0, st>>>(Crows, n, w.state);
+  KCCOT_LAUNCH_CHECK();
+  return KCCOT_OK;
+}
+
+// u for this rank's rows (written to u_rows[Brows]) from the full v[B]; then this rank's column
+// statistics colstat[2][B] = (max_i, sum_i exp2(. - max)) over its rows
+int kccot_shard_fwd_rows(const float* Crows, int Brows, int B, float eps, const float* v, float* u_rows,
+                         float* colstat, void* ws, size_t ws_bytes, void* stream) {
+  KCCOT_CHECK_ARG(Crows && v && u_rows && colstat && ws && ws_bytes >= stream_workspace_bytes(Brows, B), "bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  StreamWs w = carve(ws, Brows, B);
+  const float kscale = kLog2e / eps, ahat = -log2f((float)B);
+  stream_fwd_rows_kernel<<<w.nchunk, NT, 0, st>>>(Crows, Brows, B, kscale, ahat, v, u_rows, nullptr, w.part_a, w.part_b,
+                                                  w.state, 0);
+  KCCOT_LAUNCH_CHECK();
+  stream_colstat_reduce_kernel<<<(B + NT - 1) / NT, NT, 0, st>>>(w.part_a, w.part_b, w.nchunk, B, colstat, colstat + B);
+  KCCOT_LAUNCH_CHECK();
+  return KCCOT_OK;
+}
+
+// v[B] from the gathered statistics colstat_all[nranks][2][B]
+int kccot_shard_fwd_combine(const float* colstat_all, int nranks, int B, float* v, void* ws, void* stream) {
+  KCCOT_CHECK_ARG(colstat_all && v && ws && nranks >= 1, "bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  const float ahat = -log2f((float)B);
+  StreamState* state = (StreamState*)ws;
+  // stride between ranks is 2*B: reuse the combine kernel on interleaved views
+  stream_fwd_combine_kernel<<<(B + NT - 1) / NT, NT, 0, st>>>(colstat_all, colstat_all + B, nranks, B, ahat, v, nullptr,
+                                                             state, 2 * B);
+  KCCOT_LAUNCH_CHECK();
+  return KCCOT_OK;
+}
+
+// partial[0] = sum(pi), partial[1] = sum(pi * Chat) over this rank's rows; cost = all-reduce then
+// partial[1] * eps/log2(e) + shift * partial[0]
+int kccot_shard_cost_partial(const float* Crows, int Brows, int B, float eps, const float* u_rows, const float* v,
+                             float* partial, void* ws, void* stream) {
+  KCCOT_CHECK_ARG(Crows && u_rows && v && partial && ws, "bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  StreamState* state = (StreamState*)ws;
+  KCCOT_CUDA(cudaMemsetAsync(&state->s0, 0, 2 * sizeof(float), st));
+  stream_cost_kernel<<<min(2 * num_sms(), (Brows + 7) / 8), NT, 0, st>>>(Crows, Brows, B, kLog2e / eps, u_rows, v, state);
+  KCCOT_LAUNCH_CHECK();
+  KCCOT_CUDA(cudaMemcpyAsync(partial, &state->s0, 2 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return KCCOT_OK;
+}
+
+// seeds of the reverse pass on this rank's rows: Cbar_rows, ubar_rows, and colsum[B] (this rank's
+// part of vbar; the caller all-reduces it).  g = upstream gradient (host scalar).
+int kccot_shard_bwd_seed(const float* Crows, int Brows, int B, float eps, const float* u_rows, const float* v, float g,
+                         float* Cbar_rows, float* ubar_rows, float* colsum, void* ws, void* stream) {
+  KCCOT_CHECK_ARG(Crows && u_rows && v && Cbar_rows && ubar_rows && colsum && ws, "bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  StreamWs w = carve(ws, Brows, B);
+  // the seed kernel reads (nits, g) through device pointers: park them in the state block
+  int32_t* zero_nits = (int32_t*)((char*)ws + 64);
+  float* gdev = (float*)((char*)ws + 68);
+  KCCOT_CUDA(cudaMemsetAsync(zero_nits, 0, 4, st));
+  KCCOT_CUDA(cudaMemcpyAsync(gdev, &g, 4, cudaMemcpyHostToDevice, st));
+  stream_bwd_seed_kernel<<<w.nchunk, NT, 0, st>>>(Crows, Brows, 0, B, kLog2e / eps, 1.f / eps, u_rows, v, zero_nits, gdev,
+                                                  &w.state->shift, Cbar_rows, ubar_rows, w.part_a);
+  KCCOT_LAUNCH_CHECK();
+  stream_colsum_reduce_kernel<<<(B + NT - 1) / NT, NT, 0, st>>>(w.part_a, w.nchunk, B, colsum);
+  KCCOT_LAUNCH_CHECK();
+  return KCCOT_OK;
+}
+
+// one reverse step on this rank's rows: needs u^k (own rows), v^k, v^{k-1}, vbar (all [B]); updates
+// Cbar_rows and ubar_rows; colsum[B] = this rank's part of sum_i Pu_ij ubar_i (vbar = -all-reduce)
+int kccot_shard_bwd_rows(const float* Crows, int Brows, int B, float eps, const float* u_k_rows, const float* v_k,
+                         const float* v_km1, const float* vbar, int first, float* ubar_rows, float* Cbar_rows,
+                         float* colsum, void* ws, void* stream) {
+  KCCOT_CHECK_ARG(Crows && u_k_rows && v_k && v_km1 && vbar && ubar_rows && Cbar_rows && colsum && ws, "bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  StreamWs w = carve(ws, Brows, B);
+  stream_bwd_rows_direct_kernel<<<w.nchunk, NT, 0, st>>>(Crows, Brows, B, kLog2e / eps, -log2f((float)B), u_k_rows, v_k,
+                                                         v_km1, first, &w.state->shift, vbar, ubar_rows, Cbar_rows,
+                                                         w.part_a);
+  KCCOT_LAUNCH_CHECK();
+  stream_colsum_reduce_kernel<<<(B + NT - 1) / NT, NT, 0, st>>>(w.part_a, w.nchunk, B, colsum);
+  KCCOT_LAUNCH_CHECK();
+  return KCCOT_OK;
+}
+
+}  // extern "C"
