@@ -7,7 +7,7 @@
    ranks exchange one [2, B] (max, sum-exp) pair per rank (all-gather) and combine; the reverse pass
    exchanges plain [B] sums (all-reduce).  `ShardedSinkhorn` drives the C-ABI half-iteration kernels
    (`kccot_shard_*`) and the collectives.  The arithmetic backend is pluggable so that the partition /
-   exchange logic is testable with `gloo` on CPU (tests pass an oracle-based backend; the product
+   exchange logic is testable with `gloo` on CPU (the tests pass their own fp64 stand-in; the product
    backend is CUDA-only — there is no CPU fallback in this package).
 """
 import ctypes
