@@ -34,12 +34,13 @@ UNIT = "evals/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2_mazes")
     ap.add_argument("--kind", default="uniform", choices=["uniform", "video"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--eager", action="store_true", help="time eager Python calls instead of CUDA-graph replays")
     ap.add_argument("--cpu-budget-s", type=float, default=25.0)
     return ap.parse_args()
 
@@ -209,6 +210,24 @@ def main():
     for i in range(max(3, args.warmup)):
         step(sets[i % nsets])
     barrier()
+    # one captured graph per input set (static-buffer contract of kccotgan_b200.graphed)
+    from kccotgan_b200.graphed import GraphedSinkhornLoss
+    graphs = None
+    if not args.eager:
+        graphs = [GraphedSinkhornLoss(*[t.detach() for t in sets[i]], S, adopt=True) for i in range(nsets)]
+        for i in range(max(3, args.warmup)):
+            graphs[i % nsets].step()
+        barrier()
+        # the replayed graph must reproduce the eager result bit for bit
+        l_e, g_e = step(sets[0])
+        graphs[0].step()
+        torch.cuda.synchronize()
+        assert float(l_e) == float(graphs[0].loss), (float(l_e), float(graphs[0].loss))
+        assert torch.equal(g_e[0], graphs[0].grads["fake"])
+        config["launch"] = "CUDA-graph replay of the fused forward+backward chain (kccotgan_b200.graphed)"
+    else:
+        config["launch"] = "eager Python calls (gan_utils.compute_sinkhorn_loss + torch.autograd.grad)"
+
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -219,7 +238,10 @@ def main():
     t0 = time.perf_counter()
     e0.record()
     for i in range(args.steps):
-        step(sets[i % nsets])
+        if graphs is not None:
+            graphs[i % nsets].step()
+        else:
+            step(sets[i % nsets])
     e1.record()
     barrier()
     t1 = time.perf_counter()
@@ -231,6 +253,16 @@ def main():
         ms = float(tms)
     clocks = sampler.stop(t0, t1) if rank == 0 else None
     value = world * args.steps / (ms * 1e-3)
+    eager_evals = None
+    if graphs is not None:                          # also report the eager Python path
+        ne = max(10, min(args.steps, 200))
+        barrier()
+        e0.record()
+        for i in range(ne):
+            step(sets[i % nsets])
+        e1.record()
+        barrier()
+        eager_evals = world * ne / (e0.elapsed_time(e1) * 1e-3)
 
     # ---- e2e: host (pinned) inputs through the public API, H2D + D2H inside the timed region
     host = [[t.detach().cpu().pin_memory() for t in sets[i]] for i in range(min(nsets, 3))]
@@ -295,7 +327,7 @@ def main():
             "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32 (cost GEMMs 3xTF32 on tcgen05, fp32 accumulate)",
             "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": roofline, "cpu_baseline": cpu}
+            "roofline": roofline, "cpu_baseline": cpu, "eager_evals_per_s": eager_evals}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
