@@ -57,6 +57,7 @@ int launch_sqdist_partials_tc(const float* x, const float* y, int nprob, int Bx,
 
 // grad_tcgen05.cu — tensor-core adjoint over the stacked rows z = [x; y] (see the file header).
 // Wws: [nprob, R, R] fp32 scratch for the weight matrix.  gx / gy may be null.
+void set_grad_trace(long long* b);
 bool tc_grad_supported(const float* x, const float* y, int Bx, int By, long long K, const float* gx,
                        const float* gy);
 int launch_grad_tc(const float* Cbar3, const float* x, const float* y, int nprob, int Bx, int By, long long K,

@@ -3,37 +3,50 @@
 // With the stacked rows z = [x; y] (R = Bx + By <= 128) and a weight matrix W [R,R] built from the
 // adjoints of the cost matrices, every wanted gradient row is
 //     g_r = 2s * sum_c W_rc (z_r - z_c) = -2s * sum_c W'_rc z_c,   W' = W - diag(rowsum(W)),
-// i.e. a skinny GEMM  G^T[col, r] = sum_c Z[c, col] * W'[r, c]  streamed once over the video columns.
+// i.e. a skinny GEMM  G[r, col] = sum_c W'[r, c] * Z[c, col]  streamed once over the video columns.
 //
-//   A operand = the TMA-loaded video tile itself, MN-major.  tcgen05 accepts exactly one shared-memory
-//               layout for MN-major 32-bit operands, SWIZZLE_128B_BASE32B (32-byte chunks XOR row%4,
-//               4-row atoms): the tiles are loaded with the matching TMA mode 128B_ATOM_32B, so a
-//               [rows x 32] box is a stack of canonical atoms (SBO = 512 B), and 4 boxes side by side
-//               give M = 128 video columns (LBO = box bytes).
-//   B operand = W' (K-major SW128), split tf32 hi/lo once per CTA and resident in shared memory.
-//   3xTF32:    D += Zhi.Whi + Zlo.Whi + Zhi.Wlo, fp32 accumulate in TMEM (2 accumulator buffers).
-//   Stages alternate between the x rows and the y rows of a 128-column tile (two TMA tensors).
-//   Epilogue:  TMEM lane = video column, so for a fixed output row a warp writes 32 consecutive
-//              floats: coalesced stores straight from registers.
+//   A operand = W', split tf32 hi/lo once per CTA and parked in TENSOR MEMORY (TS-mode tcgen05.mma: lane =
+//               output row, column = contraction index; hi in columns 0-127, lo in 128-255).  An SS-mode
+//               M=128 x N=64 x K=8 instruction re-reads 4 KB of A + 2 KB of B from shared memory per 32
+//               cycles of math (~190 B/clk against a 128 B/clk port, measured as the wall with the clock64
+//               timeline); with A in TMEM only B touches shared memory (<= 64 output rows per launch).
+//   B operand = the TMA-loaded video box itself, N-major ("MN-major"): a [rows x 32] fp32 box.  tcgen05
+//               accepts exactly one shared-memory layout for MN-major 32-bit operands,
+//               SWIZZLE_128B_BASE32B (32-byte chunks XOR row%4, 4-row atoms, SBO = 512 B); the boxes
+//               are loaded with the matching TMA mode 128B_ATOM_32B, so no transposition is needed.
+//   Stage     = ONE box (8 KB + 8 KB lo at 64 rows): the ring is up to 9 deep, which is what hides the
+//               HBM latency (the first version used two 64 KB stages and starved 44 % of the time).
+//   3xTF32 in TWO instructions per k-step: B = [Zhi | Zlo] (two N-atoms, LBO = distance between the hi and
+//               lo rings), so  W'hi.[Zhi | Zlo]  is one N = 64 instruction; W'lo.Zhi (N = 32) accumulates into
+//               the first 32 columns.  The elected lane needs ~30-40 cycles per tcgen05.mma (descriptor moves
+//               to uniform registers; measured with the clock64 timeline), so fewer, fatter instructions are
+//               what keeps the tensor pipe fed.  fp32 accumulate in TMEM, 4 accumulator buffers of 64 columns.
+//   Epilogue:   TMEM lane = output row: the two warps owning lanes 0-63 add the two column halves, stage the
+//               tile in 128-byte-swizzled shared memory and one TMA store (or reduce-add) writes the
+//               [N x 32] box as full 128-byte row segments.
 #include "cost.cuh"
 #include "tc_common.cuh"
 
 namespace kccot {
 
 namespace {
-constexpr int kCols = 128;                 // video columns per work tile (UMMA M)
+constexpr int kCols = 32;                  // video columns per work tile (UMMA N) = one TMA box
 constexpr int kBoxCols = 32;               // fp32 columns per TMA box (128-byte swizzle row)
-constexpr int kMaxN = 64;                  // output rows per launch (UMMA N)
+constexpr int kMaxN = 64;                  // output rows per launch
 constexpr int kConvWarps = 8;
 constexpr int kConvThreads = kConvWarps * 32;
 constexpr int kEpiWarps = 4;
-constexpr int kThreads = 64 + kConvThreads + kEpiWarps * 32;   // 448
-constexpr int kMaxStages = 6;
-constexpr int kTmemCols = 128;             // 2 accumulator buffers x 64 columns
+constexpr int kThreads = 64 + kConvThreads + kEpiWarps * 32;   // 320
+constexpr int kMaxStages = 12;
+constexpr int kAccBufs = 4;
+constexpr int kAccCols = 64;               // per tile: [W.Zhi | W.Zlo], 32 columns each
+constexpr int kTmemCols = 512;             // W'hi [0,128) | W'lo [128,256) | 4 accumulator buffers x 64 columns
+constexpr int kTmemAcc0 = 256;
+constexpr int kObufBytes = kMaxN * 128;     // one staged output tile
 
 struct Bars {
   uint64_t full[kMaxStages], conv[kMaxStages], empty[kMaxStages];
-  uint64_t acc_full[2], acc_empty[2];
+  uint64_t acc_full[kAccBufs], acc_empty[kAccBufs];
   uint32_t tmem_base;
 };
 
@@ -80,41 +93,44 @@ __global__ void __launch_bounds__(128) build_w_pair_kernel(const float* __restri
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
-grad_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy, int Bx, int By,
-               long long K, const float* __restrict__ W, int row_off, int N, float neg2s, float* __restrict__ out,
-               int accumulate, int nstages) {
+grad_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy,
+               const __grid_constant__ CUtensorMap tmo, int Bx, int By, long long K, const float* __restrict__ W,
+               int row_off, int N, float neg2s, int accumulate, int nstages, long long* __restrict__ trace) {
   extern __shared__ uint8_t smem_raw[];
   // align by OFFSET so that the compiler keeps the shared address space (LDS/STS, not generic LD/ST)
   uint8_t* base = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int R = Bx + By;
-  const int Npad = (N + 15) & ~15;
-  const int wtiles = (R + 31) / 32;                 // 32-wide contraction tiles of W'
-  const int wtile_bytes = Npad * 128;
   const int rows_max = max(Bx, By);
-  const int box_bytes_max = rows_max * 128;
-  const int stage_bytes = 4 * box_bytes_max;        // one half (x or y rows) of a 128-column tile
-  // layout: W_hi | W_lo | stage hi[nstages] | stage lo[nstages] | barriers
-  uint8_t* w_hi = base;
-  uint8_t* w_lo = w_hi + wtiles * wtile_bytes;
-  uint8_t* st_hi = w_lo + wtiles * wtile_bytes;
+  const int stage_bytes = rows_max * 128;           // one [rows x 32] box
+  // layout: hi[nstages] | lo[nstages] | output staging | barriers   (W' lives in tensor memory)
+  uint8_t* st_hi = base;
   uint8_t* st_lo = st_hi + (size_t)nstages * stage_bytes;
-  Bars& bars = *reinterpret_cast<Bars*>(st_lo + (size_t)nstages * stage_bytes);
+  uint8_t* obuf = st_lo + (size_t)nstages * stage_bytes;      // 2 x [64 rows x 128 B] output staging (swizzled)
+  Bars& bars = *reinterpret_cast<Bars*>(obuf + 2 * kObufBytes);
 
   const int p = blockIdx.y;
+  const bool tr = (trace != nullptr) && blockIdx.x == 1 && blockIdx.y == 0;   // development timeline of one CTA
+  int trn = 0;
+#define KTRACE(role, ev) do { if (tr && trn < 64) trace[((role) * 64 + trn) * 2 + (ev)] = clock64(); } while (0)
   const long long ntiles = (K + kCols - 1) / kCols;
+  // each CTA streams a CONTIGUOUS range of column tiles: consecutive 128-byte segments of a row are
+  // fetched by the same SM back to back (DRAM page / L2 256-byte promotion locality)
+  const long long tpc = (ntiles + gridDim.x - 1) / gridDim.x;
+  const long long t_begin = blockIdx.x * tpc, t_end = min(ntiles, t_begin + tpc);
 
   if (threadIdx.x == 0) {
     tc::prefetch_tmap(&tmx);
     tc::prefetch_tmap(&tmy);
+    tc::prefetch_tmap(&tmo);
     for (int s = 0; s < nstages; ++s) {
       tc::mbar_init(&bars.full[s], 1);
-      tc::mbar_init(&bars.conv[s], kConvWarps);
+      tc::mbar_init(&bars.conv[s], 1);                      // one converter warp per box
       tc::mbar_init(&bars.empty[s], 1);
     }
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < kAccBufs; ++b) {
       tc::mbar_init(&bars.acc_full[b], 1);
-      tc::mbar_init(&bars.acc_empty[b], kEpiWarps);
+      tc::mbar_init(&bars.acc_empty[b], 2);                 // the two warps that own TMEM lanes 0-63
     }
     tc::fence_barrier_init();
   }
@@ -122,42 +138,50 @@ grad_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ 
     tc::tmem_alloc(&bars.tmem_base, kTmemCols);
     tc::tmem_relinquish();
   }
-  // W' -> shared memory, K-major 128-byte-swizzled tiles, split into tf32 hi / lo
-  {
-    const float* Wp = W + ((long long)p * R + row_off) * R;
-    const int total = wtiles * Npad * 32;
-    for (int e = threadIdx.x; e < total; e += kThreads) {
-      const int cc = e & 31, r = (e >> 5) % Npad, tw = e / (32 * Npad);
-      const int c = tw * 32 + cc;
-      const float v = (r < N && c < R) ? Wp[(long long)r * R + c] : 0.f;
-      const float h = tc::to_tf32(v);
-      const float l = tc::to_tf32(v - h);
-      const int off = tw * wtile_bytes + r * 128 + ((((cc >> 2) ^ (r & 7)) << 4) | ((cc & 3) << 2));
-      *reinterpret_cast<float*>(w_hi + off) = h;
-      *reinterpret_cast<float*>(w_lo + off) = l;
-    }
-  }
-  tc::fence_proxy_async_smem();
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem = bars.tmem_base;
+  // W' -> tensor memory.  The four epilogue warps own one 32-lane quadrant each: thread = row, 32 contraction
+  // columns per store; tf32 hi to columns [0,128), lo to [128,256).  Rows >= N and columns >= R are zero.
+  if (warp >= 2 + kConvWarps) {
+    const int quadw = warp & 3;
+    const int rr = quadw * 32 + lane;                       // A row = TMEM lane
+    const float* Wrow = W + ((long long)p * R + row_off + min(rr, N - 1)) * R;
+    for (int cg = 0; cg < 128; cg += 32) {
+      float h[32], l[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int c = cg + j;
+        const float v = (rr < N && c < R) ? Wrow[c] : 0.f;
+        h[j] = tc::to_tf32(v);
+        l[j] = tc::to_tf32(v - h[j]);
+      }
+      const uint32_t ta = tmem + ((uint32_t)(quadw * 32) << 16) + (uint32_t)cg;
+      tc::tmem_st_32x32(ta, h);
+      tc::tmem_st_32x32(ta + 128, l);
+    }
+    tc::tmem_st_wait();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
 
   if (warp == 0) {
     // ------------------------------- TMA producer ---------------------------------------------
     if (tc::elect_one()) {
       int stage = 0, phase = 0;
-      for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      for (long long t = t_begin; t < t_end; ++t) {
         const int col0 = (int)(t * kCols);
         for (int half = 0; half < 2; ++half) {
           const int rows = half ? By : Bx;
           if (rows == 0) continue;
           const CUtensorMap* tm = half ? &tmy : &tmx;
           tc::mbar_wait(&bars.empty[stage], phase ^ 1);
-          tc::mbar_arrive_expect_tx(&bars.full[stage], (uint32_t)(4 * rows * 128));
-          uint8_t* dst = st_hi + (size_t)stage * stage_bytes;
-#pragma unroll
-          for (int b = 0; b < 4; ++b) tc::tma_load_3d(tm, &bars.full[stage], dst + b * rows * 128, col0 + b * kBoxCols, 0, p);
+          KTRACE(0, 0);
+          tc::mbar_arrive_expect_tx(&bars.full[stage], (uint32_t)(rows * 128));
+          tc::tma_load_3d(tm, &bars.full[stage], st_hi + (size_t)stage * stage_bytes, col0, 0, p);
+          KTRACE(0, 1); ++trn;
           if (++stage == nstages) { stage = 0; phase ^= 1; }
         }
       }
@@ -165,100 +189,147 @@ grad_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ 
   } else if (warp == 1) {
     // ------------------------------- MMA issuer -----------------------------------------------
     if (tc::elect_one()) {
-      const uint32_t idesc = tc::make_idesc_tf32(kCols, Npad, /*A MN-major*/ 1, /*B K-major*/ 0);
-      const uint32_t whi = tc::smem_u32(w_hi), wlo = tc::smem_u32(w_lo);
+      const uint32_t idesc = tc::make_idesc_tf32(128, kAccCols, /*A K-major*/ 0, /*B MN-major*/ 1);
+      const uint32_t idesc_lo = tc::make_idesc_tf32(128, kCols, 0, 1);
+      const uint32_t lbo = (uint32_t)((size_t)nstages * stage_bytes);     // hi box -> lo box of the same stage
       int stage = 0, phase = 0;
       int ab = 0, ab_phase = 0;
-      for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      for (long long t = t_begin; t < t_end; ++t) {
         tc::mbar_wait(&bars.acc_empty[ab], ab_phase ^ 1);
         tc::tc_fence_after();
-        const uint32_t d_tmem = tmem + (uint32_t)(ab * kMaxN);
+        const uint32_t d_tmem = tmem + (uint32_t)(kTmemAcc0 + ab * kAccCols);
         bool first = true;
         for (int half = 0; half < 2; ++half) {
           const int rows = half ? By : Bx;
           if (rows == 0) continue;
-          const int c_off = half ? Bx : 0;
+          const uint32_t a_hi = tmem + (uint32_t)(half ? Bx : 0);          // W'hi columns of this half
           tc::mbar_wait(&bars.conv[stage], phase);
+          KTRACE(1, 0);
           tc::tc_fence_after();
-          const uint32_t ahi = tc::smem_u32(st_hi + (size_t)stage * stage_bytes);
-          const uint32_t alo = tc::smem_u32(st_lo + (size_t)stage * stage_bytes);
-          const uint32_t lbo = (uint32_t)rows * 128;          // bytes between the 32-column boxes
-          for (int kk = 0; kk < rows / 8; ++kk) {
-            const int c = c_off + kk * 8;                     // contraction index of this k-step
-            const uint32_t woff = (uint32_t)((c >> 5) * wtile_bytes + (c & 31) * 4);
-            const uint64_t a_h = tc::make_smem_desc(ahi + kk * 1024, lbo, 512, 1);
-            const uint64_t a_l = tc::make_smem_desc(alo + kk * 1024, lbo, 512, 1);
-            const uint64_t b_h = tc::make_smem_desc_sw128(whi + woff, 16, 1024);
-            const uint64_t b_l = tc::make_smem_desc_sw128(wlo + woff, 16, 1024);
-            tc::umma_tf32(d_tmem, a_h, b_h, idesc, first ? 0u : 1u);
-            tc::umma_tf32(d_tmem, a_l, b_h, idesc, 1u);
-            tc::umma_tf32(d_tmem, a_h, b_l, idesc, 1u);
-            first = false;
+          // N-major B over two atoms: columns 0-31 = Zhi box, 32-63 = Zlo box (LBO apart); 4-row swizzle
+          // atoms 512 B apart, 8 contraction rows per k-step
+          const uint64_t b0 = tc::make_smem_desc(tc::smem_u32(st_hi + (size_t)stage * stage_bytes), lbo, 512, 1);
+          const int nk = rows >> 3;
+#pragma unroll
+          for (int kk = 0; kk < kMaxN / 8; ++kk) {
+            if (kk < nk) {
+              const uint64_t b = b0 + (uint32_t)(kk * 64);
+              // columns 0-31 += W'hi.Zhi, columns 32-63 += W'hi.Zlo
+              tc::umma_tf32_ts(d_tmem, a_hi + kk * 8, b, idesc, first ? 0u : 1u);
+              // columns 0-31 += W'lo.Zhi
+              tc::umma_tf32_ts(d_tmem, a_hi + 128 + kk * 8, b, idesc_lo, 1u);
+              first = false;
+            }
           }
           tc::umma_commit(&bars.empty[stage]);
+          KTRACE(1, 1); ++trn;
           if (++stage == nstages) { stage = 0; phase ^= 1; }
         }
         tc::umma_commit(&bars.acc_full[ab]);
-        if (++ab == 2) { ab = 0; ab_phase ^= 1; }
+        if (++ab == kAccBufs) { ab = 0; ab_phase ^= 1; }
       }
     }
   } else if (warp < 2 + kConvWarps) {
     // ------------------------------- tf32 hi / lo split ---------------------------------------
-    const int ct = threadIdx.x - 64;
-    int stage = 0, phase = 0;
-    for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    // Warp-per-stage: converter warp cw owns every kConvWarps-th box, so up to 8 boxes are being
+    // converted at once (all warps on one box serialised the boxes at ~600 cycles each).
+    const int cw = warp - 2;
+    long long n = 0;                                          // running stage number
+    for (long long t = t_begin; t < t_end; ++t) {
       for (int half = 0; half < 2; ++half) {
         const int rows = half ? By : Bx;
         if (rows == 0) continue;
-        tc::mbar_wait(&bars.full[stage], phase);
-        const uint32_t hi = tc::smem_u32(st_hi + (size_t)stage * stage_bytes);
-        const uint32_t lo = tc::smem_u32(st_lo + (size_t)stage * stage_bytes);
-        const int n16 = 4 * rows * 8;                         // 16-byte units in this stage
-#pragma unroll 4
-        for (int e = ct; e < n16; e += kConvThreads) {
-          const float4 v = tc::lds128(hi + e * 16);
-          float4 h, l;
-          h.x = tc::to_tf32(v.x); h.y = tc::to_tf32(v.y); h.z = tc::to_tf32(v.z); h.w = tc::to_tf32(v.w);
-          l.x = tc::to_tf32(v.x - h.x); l.y = tc::to_tf32(v.y - h.y);
-          l.z = tc::to_tf32(v.z - h.z); l.w = tc::to_tf32(v.w - h.w);
-          tc::sts128(hi + e * 16, h);
-          tc::sts128(lo + e * 16, l);
+        if ((int)(n % kConvWarps) == cw) {
+          const int stage = (int)(n % nstages);
+          const int phase = (int)((n / nstages) & 1);
+          tc::mbar_wait(&bars.full[stage], phase);
+          if (cw == 0 && lane == 0) KTRACE(2, 0);
+          const uint32_t hi = tc::smem_u32(st_hi + (size_t)stage * stage_bytes);
+          const uint32_t lo = tc::smem_u32(st_lo + (size_t)stage * stage_bytes);
+          const int n16 = rows * 8;                           // 16-byte units in this box (multiple of 64)
+          for (int e0 = lane; e0 < n16; e0 += 32 * 4) {
+            float4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (e0 + 32 * u < n16) v[u] = tc::lds128(hi + (e0 + 32 * u) * 16);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int e = e0 + 32 * u;
+              if (e < n16) {
+                float4 h, l;
+                h.x = tc::to_tf32(v[u].x); h.y = tc::to_tf32(v[u].y); h.z = tc::to_tf32(v[u].z); h.w = tc::to_tf32(v[u].w);
+                l.x = tc::to_tf32(v[u].x - h.x); l.y = tc::to_tf32(v[u].y - h.y);
+                l.z = tc::to_tf32(v[u].z - h.z); l.w = tc::to_tf32(v[u].w - h.w);
+                tc::sts128(hi + e * 16, h);
+                tc::sts128(lo + e * 16, l);
+              }
+            }
+          }
+          tc::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) tc::mbar_arrive(&bars.conv[stage]);
+          if (cw == 0 && lane == 0) { KTRACE(2, 1); ++trn; }
         }
-        tc::fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) tc::mbar_arrive(&bars.conv[stage]);
-        if (++stage == nstages) { stage = 0; phase ^= 1; }
+        ++n;
       }
     }
   } else {
     // ------------------------------- epilogue --------------------------------------------------
+    // Output row r lives in TMEM lane r (< 64): only the two warps whose quadrant is 0 or 1 work.
+    // TMEM -> registers -> 128-byte-swizzled staging tile -> one TMA store (or reduce-add) of the
+    // [N x 32] box: full 128-byte row segments reach L2, columns beyond K are clipped by the tensor map.
     const int quad = warp & 3;
-    int ab = 0, ab_phase = 0;
-    float* outp = out + (long long)p * (row_off == 0 ? Bx : By) * K;
-    for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
-      tc::mbar_wait(&bars.acc_full[ab], ab_phase);
-      tc::tc_fence_after();
-      const long long col = t * kCols + quad * 32 + lane;
-      for (int g = 0; g < Npad; g += 32) {
+    if (quad < 2) {
+      const int r = quad * 32 + lane;                        // output row of this thread
+      const bool issuer = (quad == 0) && (lane == 0);
+      const bool active = quad * 32 < N;                     // warp-uniform
+      int ab = 0, ab_phase = 0;
+      int ob = 0;
+      for (long long t = t_begin; t < t_end; ++t) {
+        tc::mbar_wait(&bars.acc_full[ab], ab_phase);
+        if (issuer) KTRACE(3, 0);
+        tc::tc_fence_after();
         float d[32];
-        tc::tmem_ld_32x32(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ab * kMaxN + g), d);
-        tc::tmem_ld_wait();
-        if (col < K) {
+        if (active) {
+          float e[32];
+          const uint32_t ta = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(kTmemAcc0 + ab * kAccCols);
+          tc::tmem_ld_32x32(ta, d);
+          tc::tmem_ld_32x32(ta + 32, e);
+          tc::tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int r = g + j;
-            if (r < N) {
-              float* dst = outp + (long long)r * K + col;
-              const float v = neg2s * d[j];
-              *dst = accumulate ? (*dst + v) : v;
-            }
-          }
+          for (int j = 0; j < 32; ++j) d[j] = neg2s * (d[j] + e[j]);   // (W'.Zhi) + (W'hi.Zlo)
         }
+        if (issuer) KTRACE(4, 0);      // tmem loaded
+        tc::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&bars.acc_empty[ab]); // the accumulator is free as soon as it is in registers
+        // the staging buffer `ob` was last read by the TMA store issued two tiles ago
+        if (issuer) tc::tma_store_wait_read<1>();
+        if (issuer) KTRACE(4, 1);      // wait_read done
+        tc::named_bar_sync(2, 64);
+        if (issuer) KTRACE(5, 0);      // barrier A passed
+        if (active && r < N) {
+          const uint32_t row = tc::smem_u32(obuf + ob * kObufBytes) + r * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            tc::sts128(row + ((j ^ (r & 7)) << 4), make_float4(d[4 * j], d[4 * j + 1], d[4 * j + 2], d[4 * j + 3]));
+        }
+        if (issuer) KTRACE(5, 1);      // staged
+        tc::fence_proxy_async_smem();
+        if (issuer) KTRACE(6, 0);      // fenced
+        tc::named_bar_sync(2, 64);
+        if (issuer) KTRACE(6, 1);      // barrier B passed
+        if (issuer) {
+          const int col0 = (int)(t * kCols);
+          if (accumulate) tc::tma_reduce_add_3d(&tmo, obuf + ob * kObufBytes, col0, 0, p);
+          else tc::tma_store_3d(&tmo, obuf + ob * kObufBytes, col0, 0, p);
+          tc::tma_store_commit();
+          KTRACE(3, 1); ++trn;
+        }
+        ob ^= 1;
+        if (++ab == kAccBufs) { ab = 0; ab_phase ^= 1; }
       }
-      tc::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&bars.acc_empty[ab]);
-      if (++ab == 2) { ab = 0; ab_phase ^= 1; }
+      if (issuer) tc::tma_store_wait<0>();
     }
   }
   tc::tc_fence_before();
@@ -266,27 +337,29 @@ grad_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ 
   if (warp == 1) tc::tmem_dealloc(tmem, kTmemCols);
 }
 
+static long long* g_grad_trace = nullptr;     // development only: set through kccot_debug_set_grad_trace
 struct GradPlan { int nstages; size_t smem; };
 GradPlan plan_grad(int Bx, int By, int N) {
-  const int R = Bx + By;
-  const int Npad = (N + 15) & ~15;
-  const size_t wbytes = (size_t)2 * ((R + 31) / 32) * Npad * 128;
-  const size_t stage = (size_t)2 * 4 * (Bx > By ? Bx : By) * 128;     // hi + lo
-  const size_t budget = 227 * 1024 - 2048 - sizeof(Bars);
+  (void)N;
+  const size_t wbytes = 0;                                                 // W' lives in tensor memory
+  const size_t stage = (size_t)2 * (Bx > By ? Bx : By) * 128;              // hi + lo of one box
+  const size_t budget = 227 * 1024 - 2048 - sizeof(Bars) - 2 * kObufBytes;
   int ns = (int)((budget - wbytes) / stage);
   if (ns > kMaxStages) ns = kMaxStages;
   GradPlan g;
   g.nstages = ns;
-  g.smem = wbytes + ns * stage + sizeof(Bars) + 1024;
+  g.smem = wbytes + ns * stage + 2 * kObufBytes + sizeof(Bars) + 1024;
   return g;
 }
 }  // namespace
 
+void set_grad_trace(long long* b) { g_grad_trace = b; }
+
 bool tc_grad_supported(const float* x, const float* y, int Bx, int By, long long K, const float* gx, const float* gy) {
-  (void)gx; (void)gy;
   if (Bx % 8 || By % 8 || Bx + By > 128 || Bx > kMaxN || By > kMaxN || Bx < 8 || By < 8) return false;
-  if (K % 4 != 0 || K < kCols) return false;
+  if (K % 4 != 0 || K < 128) return false;
   if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(y) & 15)) return false;
+  if ((gx && (reinterpret_cast<uintptr_t>(gx) & 15)) || (gy && (reinterpret_cast<uintptr_t>(gy) & 15))) return false;
   return plan_grad(Bx, By, Bx > By ? Bx : By).nstages >= 2;
 }
 
@@ -294,6 +367,10 @@ bool tc_grad_supported(const float* x, const float* y, int Bx, int By, long long
 static int launch_grad_rows(const CUtensorMap& tmx, const CUtensorMap& tmy, const float* W, int nprob, int Bx, int By,
                             long long K, float s, int row_off, int N, float* out, int accumulate, cudaStream_t st) {
   const GradPlan g = plan_grad(Bx, By, N);
+  CUtensorMap tmo;     // output [nprob][N][K], box [N x 32], 128-byte swizzle (matches the staging tile)
+  if (int rc = encode_tmap_3d(&tmo, out, (uint64_t)K, (uint64_t)N, (uint64_t)nprob, (uint64_t)K * 4, (uint64_t)K * 4 * N,
+                              kBoxCols, (uint32_t)N))
+    return rc;
   static size_t attr_smem = 0;
   if (g.smem > attr_smem) {
     KCCOT_CUDA(cudaFuncSetAttribute(grad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
@@ -304,8 +381,8 @@ static int launch_grad_rows(const CUtensorMap& tmx, const CUtensorMap& tmy, cons
   if (gx > ntiles) gx = (int)ntiles;
   if (gx < 1) gx = 1;
   dim3 grid(gx, nprob);
-  grad_tc_kernel<<<grid, kThreads, g.smem, st>>>(tmx, tmy, Bx, By, K, W, row_off, N, -2.f * s, out, accumulate,
-                                                g.nstages);
+  grad_tc_kernel<<<grid, kThreads, g.smem, st>>>(tmx, tmy, tmo, Bx, By, K, W, row_off, N, -2.f * s, accumulate,
+                                                g.nstages, g_grad_trace);
   KCCOT_LAUNCH_CHECK();
   return KCCOT_OK;
 }
@@ -349,3 +426,6 @@ int launch_grad_pair_tc(const float* Cbar, const float* x, const float* y, int n
 }
 
 }  // namespace kccot
+
+// development only: device buffer of 4 roles x 64 records x 2 timestamps (clock64) filled by CTA 1
+extern "C" void kccot_debug_set_grad_trace(long long* buf) { kccot::set_grad_trace(buf); }

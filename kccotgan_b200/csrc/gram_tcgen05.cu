@@ -100,7 +100,7 @@ sqdist_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
     }
   } else if (warp == 1) {
     // ------------------------------- MMA issuer -----------------------------------------------
-    if (tc::elect_one()) {
+    {   // the whole warp runs this loop with uniform operands; one elected lane issues each instruction
       const uint32_t idesc = tc::make_idesc_tf32(128, N, 0, 0);
       int stage = 0, phase = 0, acc_phase = 0;
       for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
@@ -118,12 +118,12 @@ sqdist_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
             const uint64_t dh = tc::make_smem_desc_sw128(hi_addr + k4 * 32, 16, 1024);
             const uint64_t dl = tc::make_smem_desc_sw128(lo_addr + k4 * 32, 16, 1024);
             const int step = (kb - kb0) * (kKB / 8) + k4;
-            tc::umma_tf32(tmem + (uint32_t)((step % 3) * kRows), dh, dh, idesc, step >= 3 ? 1u : 0u);
-            tc::umma_tf32(tmem + (uint32_t)(3 * kRows), dh, dl, idesc, step > 0 ? 1u : 0u);
-            tc::umma_tf32(tmem + (uint32_t)(3 * kRows), dl, dh, idesc, 1u);
+            tc::umma_tf32_warp(tmem + (uint32_t)((step % 3) * kRows), dh, dh, idesc, step >= 3 ? 1u : 0u);
+            tc::umma_tf32_warp(tmem + (uint32_t)(3 * kRows), dh, dl, idesc, step > 0 ? 1u : 0u);
+            tc::umma_tf32_warp(tmem + (uint32_t)(3 * kRows), dl, dh, idesc, 1u);
           }
-          tc::umma_commit(&S.empty[stage]);
-          if (kb == kb1 - 1) tc::umma_commit(&S.acc_full);
+          tc::umma_commit_warp(&S.empty[stage]);
+          if (kb == kb1 - 1) tc::umma_commit_warp(&S.acc_full);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
         acc_phase ^= 1;
