@@ -246,6 +246,8 @@ def main():
     barrier()
     t1 = time.perf_counter()
     launches = lib.kccot_launch_count() - launches0
+    if graphs is not None:
+        launches = args.steps * graphs[0].kernels_per_replay      # replays do not pass through the C-ABI counter
     ms = e0.elapsed_time(e1)
     if world > 1:
         tms = torch.tensor([ms], device=dev)
@@ -306,12 +308,20 @@ def main():
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
     stages = stage_times(lib, F, torch, sets, B, K, T, dev)
     # algorithmic bytes: forward distances read X,Y once (8BK); adjoint reads X,Y and writes g_fake (12BK)
-    alg = {"sqdist_tc_kernel": 8.0 * B * K, "grad_tc_kernel": 12.0 * B * K}
+    alg = {"sqdist_tc_kernel": 8.0 * B * K, "grad_tc_kernel(+W build)": 12.0 * B * K}
+    traffic = {}
+    try:        # DRAM bytes per launch from the committed `ncu --set full` capture of the same kernels
+        with open(os.path.join(ROOT, "profiles", "r1_dram_traffic.json")) as f:
+            traffic = json.load(f)
+    except OSError:
+        pass
     dom = max(alg, key=lambda k: stages.get(k, 0.0))
     dur_us = stages[dom]
     achieved = alg[dom] / (dur_us * 1e-6) / 1e9
     roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / hbm_peak, "traffic": traffic.get(dom.split("(")[0]), "peak_source": peak_src,
+                "other_hbm_kernels": {k: {"achieved_GBps": alg[k] / (stages[k] * 1e-6) / 1e9,
+                                          "frac": alg[k] / (stages[k] * 1e-6) / 1e9 / hbm_peak} for k in alg if k != dom},
                 "algorithmic_bytes_per_launch": alg[dom], "avg_launch_us": dur_us,
                 "stage_us": stages,
                 "whole_eval": {"algorithmic_bytes": 20.0 * B * K + 40.0 * B * T * 8,
@@ -333,7 +343,7 @@ def main():
         dist.destroy_process_group()
 
 
-def stage_times(lib, F, torch, sets, B, K, T, dev, reps=12):
+def stage_times(lib, F, torch, sets, B, K, T, dev, reps=40):
     """CUDA-event time of each stage of one eval, called through the C ABI, inputs cold in L2."""
     from kccotgan_b200 import _lib
     J = 8
@@ -387,19 +397,19 @@ def stage_times(lib, F, torch, sets, B, K, T, dev, reps=12):
     out = {}
     for name, fn in (("sqdist_tc_kernel", f_partials), ("cost_fwd(sqdist+finalize)", f_cost),
                      ("sinkhorn_fwd_small_kernel", f_skf), ("sinkhorn_bwd_small_kernel", f_skb),
-                     ("cost_bwd(W+grad+martingale)", f_grad), ("grad_tc_kernel", f_grad_only)):
+                     ("cost_bwd(W+grad+martingale)", f_grad), ("grad_tc_kernel(+W build)", f_grad_only)):
         for i in range(3):
             fn(i)
         torch.cuda.synchronize()
-        tot = 0.0
+        # back-to-back launches (input sets rotate, so the videos are cold in L2): launch latency overlaps
+        # execution and the event pair brackets `reps` launches on the launching stream
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
         for i in range(reps):
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
             fn(i + 3)
-            b.record()
-            torch.cuda.synchronize()
-            tot += a.elapsed_time(b)
-        out[name] = tot / reps * 1e3
+        b.record()
+        torch.cuda.synchronize()
+        out[name] = a.elapsed_time(b) / reps * 1e3
     # grad_only still includes the tiny W-build kernel (~2 us); the ncu launch list separates them
     return out
 

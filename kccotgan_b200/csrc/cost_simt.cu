@@ -228,47 +228,148 @@ int launch_cost_bwd_simt(const float* W, long long sr, long long sc, long long w
 //   F mode 0 (gradient of h, F from M): M[k,t+1,c] - M[k,t,c] for t < T-1, else 0
 //   F mode 1 (gradient of M, F from h): h[k,t-1,c] [t>=1] - h[k,t,c] [t<=T-2]
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ float mart_factor(const float* X, int mode, int t, int T, int J, int q) {
-  if (mode == 0) return (t < T - 1) ? X[q + J] - X[q] : 0.f;
-  return ((t >= 1) ? X[q - J] : 0.f) - ((t <= T - 2) ? X[q] : 0.f);
-}
+constexpr int MR = 4;          // output rows per CTA
+constexpr int MKC = 64;        // contraction chunk staged in shared memory
 
-__global__ void __launch_bounds__(128) martingale_bwd_kernel(MartJobs jobs, int T, int J, float s) {
-  extern __shared__ float wrow[];      // [2][ncontr]
+// One CTA = one job, MR consecutive output rows, all T*J columns.  The difference operator commutes
+// with the contraction: out[r, q] = s * (m1 * G[r, q + d1] - m2 * G[r, q + d2]) with the plain product
+// G = W X over the RAW rows of X (M or h), so nothing but X and the MR weight rows is staged: both
+// sources' blocks are fetched with one batch of independent 16-byte loads, every thread owns a few
+// (row, column) entries of G, and the differences are taken once at the end through shared memory.
+// History: v0 walked global memory with two dependent loads per FMA (~45 us for 80 KFLOP); v1 staged
+// a materialised factor matrix F and spent 60 % of its 19 us building it (ncu source view, r42).
+__global__ void __launch_bounds__(256) martingale_bwd_kernel(MartJobs jobs, int T, int J, float s) {
+  extern __shared__ float4 sh4[];
+  float* sh = reinterpret_cast<float*>(sh4);     // X[2][MKC*TJ] | W[2][MR*MKC];  G[MR*TJ] aliases X at the end
   const MartJob& jb = jobs.j[blockIdx.y];
-  const int r = blockIdx.x, p = blockIdx.z;
-  if (r >= jb.nrows || jb.out == nullptr) return;
+  const int r0 = blockIdx.x * MR, p = blockIdx.z;
+  if (r0 >= jb.nrows || jb.out == nullptr) return;
   const int TJ = T * J;
-  for (int src = 0; src < 2; ++src) {
-    const float* C = src ? jb.C2 : jb.C1;
-    if (C == nullptr) continue;
-    C += (long long)p * jb.cprob;
-    for (int k = threadIdx.x; k < jb.ncontr; k += blockDim.x)
-      wrow[src * jb.ncontr + k] = jb.transposed ? C[(long long)k * jb.ld + r] : C[(long long)r * jb.ld + k];
+  const int nout = MR * TJ;
+  float* Wbase = sh + 2 * MKC * TJ;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  float acc[8];
+  int wof[8], qof[8];                              // per-output offsets: weight row, column
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    acc[u] = 0.f;
+    const int o = threadIdx.x + u * 256;
+    const int rr = (o < nout) ? o / TJ : 0;
+    wof[u] = rr * MKC;
+    qof[u] = o - rr * TJ;
+  }
+  for (int k0 = 0; k0 < jb.ncontr; k0 += MKC) {
+    const int kc = min(MKC, jb.ncontr - k0);
+    const int n = kc * TJ;
+    __syncthreads();
+    for (int src = 0; src < 2; ++src) {
+      const float* C = src ? jb.C2 : jb.C1;
+      if (C == nullptr) continue;
+      C += (long long)p * jb.cprob;
+      const float* X = (src ? jb.X2 : jb.X1) + ((long long)p * jb.ncontr + k0) * TJ;   // kc contiguous raw rows
+      float* Xs = sh + src * MKC * TJ;
+      float* Ws = Wbase + src * MR * MKC;
+      if ((n & 3) == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0) {
+        const float4* X4 = reinterpret_cast<const float4*>(X);
+        float4* Xs4 = reinterpret_cast<float4*>(Xs);
+        constexpr int kBatch = 8;
+        for (int e0 = threadIdx.x; e0 < (n >> 2); e0 += 256 * kBatch) {
+          float4 v[kBatch];
+#pragma unroll
+          for (int u = 0; u < kBatch; ++u) {
+            const int e = e0 + u * 256;
+            if (e < (n >> 2)) v[u] = X4[e];
+          }
+#pragma unroll
+          for (int u = 0; u < kBatch; ++u) {
+            const int e = e0 + u * 256;
+            if (e < (n >> 2)) Xs4[e] = v[u];
+          }
+        }
+      } else {
+        for (int e = threadIdx.x; e < n; e += 256) Xs[e] = X[e];
+      }
+      for (int rr = warp; rr < MR; rr += nwarps) {
+        const int r = r0 + rr;
+        for (int k = lane; k < kc; k += 32) {
+          float w = 0.f;
+          if (r < jb.nrows) w = jb.transposed ? C[(long long)(k0 + k) * jb.ld + r] : C[(long long)r * jb.ld + k0 + k];
+          Ws[rr * MKC + k] = w;
+        }
+      }
+    }
+    __syncthreads();
+    for (int src = 0; src < 2; ++src) {
+      if ((src ? jb.C2 : jb.C1) == nullptr) continue;
+      const float* Xs = sh + src * MKC * TJ;
+      const float* Ws = Wbase + src * MR * MKC;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        if (threadIdx.x + u * 256 < nout) {
+          const float* wr = Ws + wof[u];
+          const float* fc = Xs + qof[u];
+          float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+          int k = 0;
+          for (; k + 8 <= kc; k += 8) {                 // 10 independent shared-memory loads per chain step
+            const float4 w0 = *reinterpret_cast<const float4*>(wr + k);
+            const float4 w1 = *reinterpret_cast<const float4*>(wr + k + 4);
+            const float f0 = fc[(k + 0) * TJ], f1 = fc[(k + 1) * TJ], f2 = fc[(k + 2) * TJ], f3 = fc[(k + 3) * TJ];
+            const float f4 = fc[(k + 4) * TJ], f5 = fc[(k + 5) * TJ], f6 = fc[(k + 6) * TJ], f7 = fc[(k + 7) * TJ];
+            a0 = fmaf(w0.x, f0, a0); a1 = fmaf(w0.y, f1, a1); a2 = fmaf(w0.z, f2, a2); a3 = fmaf(w0.w, f3, a3);
+            a0 = fmaf(w1.x, f4, a0); a1 = fmaf(w1.y, f5, a1); a2 = fmaf(w1.z, f6, a2); a3 = fmaf(w1.w, f7, a3);
+          }
+          for (; k < kc; ++k) a0 = fmaf(wr[k], fc[k * TJ], a0);
+          acc[u] += (a0 + a1) + (a2 + a3);
+        }
+      }
+    }
+  }
+  // G -> shared memory, then the (masked) differences of mart_factor applied to G's columns
+  __syncthreads();
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const int o = threadIdx.x + u * 256;
+    if (o < nout) sh[o] = acc[u];
   }
   __syncthreads();
-  float* out = jb.out + ((long long)p * jb.nrows + r) * TJ;
-  for (int q = threadIdx.x; q < TJ; q += blockDim.x) {
-    const int t = q / J;
-    float a = 0.f;
-    for (int src = 0; src < 2; ++src) {
-      const float* X = src ? jb.X2 : jb.X1;
-      if ((src ? jb.C2 : jb.C1) == nullptr) continue;
-      X += (long long)p * jb.ncontr * TJ;
-      const float* w = wrow + src * jb.ncontr;
-      for (int k = 0; k < jb.ncontr; ++k) a = fmaf(w[k], mart_factor(X + (long long)k * TJ, jb.mode, t, T, J, q), a);
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const int o = threadIdx.x + u * 256;
+    if (o < nout) {
+      const int rr = wof[u] / MKC, q = qof[u];
+      const int r = r0 + rr;
+      if (r < jb.nrows) {
+        const int t = q / J;
+        const float* g = sh + rr * TJ;
+        float v;
+        if (jb.mode == 0) v = (t < T - 1) ? g[q + J] - g[q] : 0.f;
+        else v = ((t >= 1) ? g[q - J] : 0.f) - ((t <= T - 2) ? g[q] : 0.f);
+        v *= s;
+        float* dst = jb.out + ((long long)p * jb.nrows + r) * TJ + q;
+        *dst = jb.acc ? *dst + v : v;
+      }
     }
-    const float v = s * a;
-    out[q] = jb.acc ? out[q] + v : v;
   }
 }
 
 int launch_martingale_jobs(const MartJobs& jobs, int njobs, int nprob, int T, int J, float s, cudaStream_t st) {
-  int maxrows = 0, maxc = 0;
-  for (int i = 0; i < njobs; ++i) { maxrows = max(maxrows, jobs.j[i].nrows); maxc = max(maxc, jobs.j[i].ncontr); }
+  int maxrows = 0;
+  for (int i = 0; i < njobs; ++i)
+    if (jobs.j[i].out) maxrows = max(maxrows, jobs.j[i].nrows);
   if (maxrows == 0) return KCCOT_OK;
-  dim3 grid(maxrows, njobs, nprob);
-  martingale_bwd_kernel<<<grid, 128, (size_t)2 * maxc * sizeof(float), st>>>(jobs, T, J, s);
+  const int TJ = T * J;
+  const size_t smem = (size_t)(2 * MKC * TJ + 2 * MR * MKC) * sizeof(float);
+  if (MR * TJ > 8 * 256 || smem > 200 * 1024) {
+    set_error("martingale adjoint: T*J = %d too large (max %d)", TJ, 8 * 256 / MR);
+    return KCCOT_EINVAL;
+  }
+  static size_t attr = 48 * 1024;
+  if (smem > attr) {
+    KCCOT_CUDA(cudaFuncSetAttribute(martingale_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr = 200 * 1024;
+  }
+  dim3 grid((maxrows + MR - 1) / MR, njobs, nprob);
+  martingale_bwd_kernel<<<grid, 256, smem, st>>>(jobs, T, J, s);
   KCCOT_LAUNCH_CHECK();
   return KCCOT_OK;
 }

@@ -13,7 +13,8 @@ int launch_sinkhorn_fwd_small(const float* C, int nsolve, int B, float eps, int 
                               cudaStream_t st);
 int launch_sinkhorn_bwd_small(const float* C, int nsolve, int B, float eps, int L, const float* u_hist,
                               const float* v_hist, const int32_t* nits, const float* gcost, float* Cbar,
-                              cudaStream_t st);
+                              const int32_t* only_if, cudaStream_t st);
+
 
 // sinkhorn_stream.cu — any B; C streamed from L2/HBM; a kernel boundary per half-iteration pair.
 struct StreamState {

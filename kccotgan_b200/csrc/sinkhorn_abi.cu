@@ -6,8 +6,8 @@ using namespace kccot;
 extern "C" {
 
 size_t kccot_sinkhorn_workspace_bytes(int nsolve, int B, int L) {
-  (void)nsolve; (void)L;
-  if (B <= kSmallSinkhornMaxB) return 256;
+  (void)L;
+  if (B <= kSmallSinkhornMaxB) return align_up(256 + (size_t)(nsolve > 0 ? nsolve : 1) * sizeof(int32_t), 256);
   return stream_workspace_bytes(B, B);
 }
 
@@ -36,7 +36,7 @@ int kccot_sinkhorn_bwd(const float* C, int nsolve, int B, float eps, int L, cons
   KCCOT_CHECK_ARG(nsolve >= 1 && B >= 1 && L >= 0 && eps > 0.f, "bad sizes");
   cudaStream_t st = (cudaStream_t)stream;
   if (B <= kSmallSinkhornMaxB)
-    return launch_sinkhorn_bwd_small(C, nsolve, B, eps, L, u_hist, v_hist, nits, gcost, Cbar, st);
+    return launch_sinkhorn_bwd_small(C, nsolve, B, eps, L, u_hist, v_hist, nits, gcost, Cbar, nullptr, st);
   KCCOT_CHECK_ARG(ws && ws_bytes >= stream_workspace_bytes(B, B), "workspace too small");
   for (int n = 0; n < nsolve; ++n) {
     const long long hs = (long long)(L + 1) * B;

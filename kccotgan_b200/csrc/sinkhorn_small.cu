@@ -200,7 +200,64 @@ __global__ void __launch_bounds__(4 * 4 * EPT) sinkhorn_fwd_small_kernel(
   float u_cur = 0.f;            // uhat of this thread's row (all four lanes of a row hold it)
   bool slow = false;
   int it = 0, nits = 0;
+  // iterations before `first_check` can never stop (gan_utils.py:159 needs nits >= Lmin, :116 needs the
+  // index >= Lmin; the last iteration needs no test): they run in a tight loop without the bookkeeping
+  const int first_check = min(L - 1, exit_on_index ? Lmin : Lmin - 1);
   for (;;) {
+    if (!slow) {
+      // Fixed-point short cut: the iteration is a deterministic function of the column scalings b, so
+      // once an iteration returns b bit-for-bit (fp32 Sinkhorn does: after 1 iteration on the
+      // diagonal-dominant xx / yy problems, after 55-70 on cfg2's uniform xy problem) every later
+      // iteration reproduces the same potentials; the remaining history rows are copies.  The test
+      // rides on the barrier that ends the iteration.
+      float b_prev = __int_as_float(0x7fc00000);
+      for (; it < first_check; ++it) {
+        const float s = dot_slice<EPT>(Kr, bs_q);
+        if (bad_flag) break;                              // set during iteration it-1: rolled back below
+        const float a_new = two_ahat * fast_rcp(s);       // critical path first
+        const float unew = ahat + alpha - fast_log2(s);
+        if (owner) {
+          as[ip] = a_new;
+          urow(it + 1)[i] = unew;
+          if (!HS) uh[(long long)(it + 1) * B + i] = unew;
+          if (!(s > kLo && s < kHi)) bad_flag = 1;
+        }
+        __syncthreads();
+        const float t = dot_slice<EPT>(Kc, as_q);
+        const float b_new = two_ahat * fast_rcp(t);
+        const float vnew = ahat - fast_log2(t);
+        if (owner) {
+          bs[ip] = b_new;
+          vrow(it + 1)[i] = vnew;
+          if (!HS) vh[(long long)(it + 1) * B + i] = vnew;
+          if (!(t > kLo && t < kHi)) bad_flag = 1;
+        }
+        const int fixed = __syncthreads_and((i >= B) | (b_new == b_prev));
+        b_prev = b_new;
+        if (fixed && !bad_flag) {
+          if (owner)
+            for (int r = it + 2; r <= first_check; ++r) {
+              if (HS) { urow(r)[i] = unew; vrow(r)[i] = vnew; }
+              else { uh[(long long)r * B + i] = unew; vh[(long long)r * B + i] = vnew; }
+            }
+          it = first_check;
+          break;
+        }
+      }
+      nits = it;
+      if (bad_flag) {                                     // iteration it-1 left the safe range: redo it in the log domain
+        slow = true;
+        it = max(it - 1, 0);
+        __syncthreads();
+        if (!HS && tid < B) { us[tid] = uh[(long long)it * B + tid]; vs[tid] = vh[(long long)it * B + tid]; }
+        __syncthreads();
+      } else if (!HS && owner) {
+        us[i] = uh[(long long)it * B + i];                // the tight loop does not maintain us / vs
+        vs[i] = vh[(long long)it * B + i];
+      }
+      __syncthreads();
+      u_cur = urow(it)[ic];
+    }
     while (it < L) {
       float du;
       if (!slow) {
@@ -315,7 +372,8 @@ template <int EPT, bool HS>
 __global__ void __launch_bounds__(4 * 4 * EPT) sinkhorn_bwd_small_kernel(
     const float* __restrict__ C, int B, float eps, int L, const float* __restrict__ u_hist,
     const float* __restrict__ v_hist, const int32_t* __restrict__ nits_in, const float* __restrict__ gcost,
-    float* __restrict__ Cbar) {
+    float* __restrict__ Cbar, const int32_t* __restrict__ only_if) {
+  if (only_if != nullptr && only_if[blockIdx.x] == 0) return;     // fallback launch: only the declined problems
   constexpr int BM = 4 * EPT;
   constexpr int PQ = EPT + 4;                           // padded chunk stride (see pad_index)
   constexpr int BMP = 4 * PQ;
@@ -561,7 +619,8 @@ int launch_sinkhorn_fwd_small(const float* C, int nsolve, int B, float eps, int 
 
 template <int EPT>
 static int launch_bwd_t(const float* C, int nsolve, int B, float eps, int L, const float* u_hist, const float* v_hist,
-                        const int32_t* nits, const float* gcost, float* Cbar, int threads, cudaStream_t st) {
+                        const int32_t* nits, const float* gcost, float* Cbar, const int32_t* only_if, int threads,
+                        cudaStream_t st) {
   const size_t hist_bytes = (size_t)2 * (L + 1) * 4 * (EPT + 4) * sizeof(float);
   if (hist_bytes <= 160 * 1024) {
     static size_t attr = 0;
@@ -570,9 +629,10 @@ static int launch_bwd_t(const float* C, int nsolve, int B, float eps, int L, con
                                       (int)(160 * 1024)));
       attr = 160 * 1024;
     }
-    sinkhorn_bwd_small_kernel<EPT, true><<<nsolve, threads, hist_bytes, st>>>(C, B, eps, L, u_hist, v_hist, nits, gcost, Cbar);
+    sinkhorn_bwd_small_kernel<EPT, true><<<nsolve, threads, hist_bytes, st>>>(C, B, eps, L, u_hist, v_hist, nits, gcost, Cbar,
+                                                                          only_if);
   } else {
-    sinkhorn_bwd_small_kernel<EPT, false><<<nsolve, threads, 0, st>>>(C, B, eps, L, u_hist, v_hist, nits, gcost, Cbar);
+    sinkhorn_bwd_small_kernel<EPT, false><<<nsolve, threads, 0, st>>>(C, B, eps, L, u_hist, v_hist, nits, gcost, Cbar, only_if);
   }
   KCCOT_LAUNCH_CHECK();
   return KCCOT_OK;
@@ -580,10 +640,10 @@ static int launch_bwd_t(const float* C, int nsolve, int B, float eps, int L, con
 
 int launch_sinkhorn_bwd_small(const float* C, int nsolve, int B, float eps, int L, const float* u_hist,
                               const float* v_hist, const int32_t* nits, const float* gcost, float* Cbar,
-                              cudaStream_t st) {
+                              const int32_t* only_if, cudaStream_t st) {
   const int threads = ((4 * B + 31) / 32) * 32;
-  if (B <= 32) return launch_bwd_t<8>(C, nsolve, B, eps, L, u_hist, v_hist, nits, gcost, Cbar, threads, st);
-  return launch_bwd_t<16>(C, nsolve, B, eps, L, u_hist, v_hist, nits, gcost, Cbar, threads, st);
+  if (B <= 32) return launch_bwd_t<8>(C, nsolve, B, eps, L, u_hist, v_hist, nits, gcost, Cbar, only_if, threads, st);
+  return launch_bwd_t<16>(C, nsolve, B, eps, L, u_hist, v_hist, nits, gcost, Cbar, only_if, threads, st);
 }
 
 }  // namespace kccot

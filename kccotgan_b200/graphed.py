@@ -39,10 +39,13 @@ class GraphedSinkhornLoss:
             for _ in range(max(1, warmup)):
                 self._eager()
         torch.cuda.current_stream(dev).wait_stream(side)
+        from . import _lib
+        n0 = _lib.load().kccot_launch_count()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.loss, g = self._eager()
             self.grads = dict(zip(self._leaf_names, g))
+        self.kernels_per_replay = int(_lib.load().kccot_launch_count() - n0)   # libkccot kernels in the graph
 
     def _eager(self):
         loss = gan_utils.compute_sinkhorn_loss(self.real, self.fake, self.scaling_coef, 0.8, 100, self.h_fake,

@@ -222,6 +222,41 @@ def test_sinkhorn_kernels_vs_oracle(B, eps, L):
         assert e < GRAD_TOL
 
 
+@pytest.mark.parametrize("B,L,kind", [(64, 100, "diag"), (40, 100, "diag"), (64, 400, "diag"), (64, 100, "slow"),
+                                      (24, 100, "slow"), (64, 10, "diag")])
+def test_sinkhorn_history_fixed_point(B, L, kind):
+    """The forward kernel stops iterating once the fp32 scalings repeat bit for bit and fills the rest of
+    the history with copies (sinkhorn_small.cu): every saved row must still equal the potentials the
+    reference's L iterations produce.  "diag" reaches the fixed point after one iteration (the xx / yy
+    problems of the mixed loss), "slow" after some tens of iterations."""
+    from kccotgan_b200 import _lib, functional as F
+    from oracle import closed_form as cf
+    rng = np.random.default_rng(7 * B + L)
+    if kind == "diag":
+        C = (500.0 * (1.0 - np.eye(B)) + rng.random((B, B))).astype(np.float32)
+    else:
+        C = (1350.0 + 30.0 * rng.random((B, B))).astype(np.float32)
+    Ct = torch.from_numpy(C[None]).cuda()
+    uh = torch.full((1, L + 1, B), float("nan"), device="cuda")
+    vh = torch.full((1, L + 1, B), float("nan"), device="cuda")
+    nits = torch.zeros(1, dtype=torch.int32, device="cuda")
+    cost = torch.zeros(1, device="cuda")
+    ws = torch.empty(_lib.load().kccot_sinkhorn_workspace_bytes(1, B, L), dtype=torch.uint8, device="cuda")
+    _lib.call("kccot_sinkhorn_fwd", F._ptr(Ct), 1, B, 1.0, L, 100, 1e-2, 0, F._ptr(uh), F._ptr(vh), F._ptr(nits),
+              F._ptr(cost), F._ptr(ws), ws.numel(), F._stream(Ct.device))
+    C64 = C.astype(np.float64)
+    ref, ruh, rvh, rn = cf.sinkhorn_forward(C64 - C64.min(), 1.0, L, Lmin=100, thresh=1e-2)
+    assert int(nits[0]) == rn
+    ln2 = np.log(2.0)                                   # saved potentials are in log2 units of the shifted cost
+    gu, gv = uh[0, : rn + 1].cpu().numpy() * ln2, vh[0, : rn + 1].cpu().numpy() * ln2
+    assert np.isfinite(gu).all() and np.isfinite(gv).all()
+    scale = max(np.abs(ruh).max(), np.abs(rvh).max(), 1.0)
+    eu, ev = np.abs(gu - ruh[: rn + 1]).max() / scale, np.abs(gv - rvh[: rn + 1]).max() / scale
+    print(kind, B, L, "nits", rn, "history err", eu, ev)
+    assert eu < 1e-5 and ev < 1e-5
+    assert abs(float(cost[0]) - (ref + C64.min())) <= LOSS_TOL * abs(ref + C64.min())
+
+
 @pytest.mark.parametrize("B,eps,L", [(24, 0.02, 30), (64, 0.05, 120), (40, 0.01, 10)])
 def test_sinkhorn_guard_path(B, eps, L):
     """Ill-scaled problems (spread/eps in the hundreds) leave the fp32 range of the scaling form: the
