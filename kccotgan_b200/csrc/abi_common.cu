@@ -27,6 +27,28 @@ int num_sms() {
   }
   return cached;
 }
+
+// A second stream (plus fork / join events) per host thread and device, for the one place where two
+// independent kernels of a call can overlap (martingale adjoint next to the gradient GEMM).  Works under
+// stream capture too: waiting on the captured fork event pulls the side stream into the capture, the
+// join event brings it back before the call returns.
+SideLane* side_lane() {
+  constexpr int kMaxDev = 64;
+  static thread_local SideLane lanes[kMaxDev];
+  static thread_local bool ready[kMaxDev] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDev) return nullptr;
+  if (!ready[dev]) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    (void)cs;
+    SideLane& l = lanes[dev];
+    if (cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&l.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&l.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    ready[dev] = true;
+  }
+  return &lanes[dev];
+}
 }  // namespace kccot
 
 extern "C" {

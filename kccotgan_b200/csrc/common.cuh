@@ -45,6 +45,12 @@ inline void count_launch(int n = 1) { g_launches.fetch_add((unsigned long long)n
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 int num_sms();
 
+struct SideLane {
+  cudaStream_t stream;
+  cudaEvent_t fork, join;
+};
+SideLane* side_lane();   // per host thread and device; nullptr if the stream / events cannot be created
+
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 

@@ -14,6 +14,7 @@ struct CostBlock {
   float* C;
   long long C_prob_stride;
   int Bx, By, zero_diag;
+  int sym;                 // partials hold only hi.lo^T of the cross terms: C_ij = (P_ij + P_ji) / 2 (tensor-core path)
 };
 struct CostBlocks {
   CostBlock b[3];

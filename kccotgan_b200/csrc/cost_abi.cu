@@ -75,7 +75,7 @@ int kccot_cost_fwd(const float* x, const float* y, int nprob, int Bx, int By, lo
     if (int rc = launch_sqdist_partials_tc(x, same ? nullptr : y, nprob, Bx, same ? 0 : By, K, ks, kbps, (float*)ws, st))
       return rc;
     b.prob_stride = (long long)ks * kTcTile; b.ks_stride = kTcTile; b.ld = 128; b.nks = ks;
-    b.row_off = 0; b.col_off = same ? 0 : Bx;
+    b.row_off = 0; b.col_off = same ? 0 : Bx; b.sym = 1;
   } else {
     int ks;
     long long slab;
@@ -127,7 +127,7 @@ int kccot_mixed_cost_fwd(const float* real, const float* fake, int nprob, int B,
     for (int q = 0; q < 3; ++q) {
       CostBlock& b = blocks.b[q];
       b.part = (const float*)ws; b.prob_stride = (long long)ks * kTcTile; b.ks_stride = kTcTile; b.ld = 128;
-      b.nks = ks; b.row_off = roff[q]; b.col_off = coff[q];
+      b.nks = ks; b.row_off = roff[q]; b.col_off = coff[q]; b.sym = 1;
     }
   } else {
     int ks;
@@ -239,20 +239,6 @@ int kccot_mixed_cost_bwd(const float* Cbar3, const float* real, const float* fak
     set_error("tcgen05 gradient path requested but unsupported for B=%d K=%lld", B, K);
     return KCCOT_EUNSUPPORTED;
   }
-  if (tc_ok) {
-    if (int rc = launch_grad_tc(Cbar3, real, fake, nprob, B, B, K, s, g_real, g_fake, acc, (float*)ws, st)) return rc;
-  } else {
-    if (g_fake) {
-      if (int rc = launch_cost_bwd_simt(Cxy, 1, B, cprob, fake, real, nprob, B, B, K, s, g_fake, acc, st)) return rc;
-      if (int rc = launch_cost_bwd_simt(Cyy, B, 1, cprob, fake, fake, nprob, B, B, K, s, g_fake, 1, st)) return rc;
-      if (int rc = launch_cost_bwd_simt(Cyy, 1, B, cprob, fake, fake, nprob, B, B, K, s, g_fake, 1, st)) return rc;
-    }
-    if (g_real) {
-      if (int rc = launch_cost_bwd_simt(Cxy, B, 1, cprob, real, fake, nprob, B, B, K, s, g_real, acc, st)) return rc;
-      if (int rc = launch_cost_bwd_simt(Cxx, B, 1, cprob, real, real, nprob, B, B, K, s, g_real, 1, st)) return rc;
-      if (int rc = launch_cost_bwd_simt(Cxx, 1, B, cprob, real, real, nprob, B, B, K, s, g_real, 1, st)) return rc;
-    }
-  }
   // martingale terms: xy = (h_fake, m_real), xx = (h_real, m_real), yy = (h_fake, m_fake) — one launch
   MartJobs jobs{};
   const int Bi = B;
@@ -260,6 +246,32 @@ int kccot_mixed_cost_bwd(const float* Cbar3, const float* real, const float* fak
   jobs.j[1] = MartJob{gm_real, Cxy, h_fake, Cxx, h_real, cprob, Bi, Bi, Bi, 1, 1, acc};
   jobs.j[2] = MartJob{gh_real, Cxx, m_real, nullptr, nullptr, cprob, Bi, Bi, Bi, 0, 0, acc};
   jobs.j[3] = MartJob{gm_fake, Cyy, h_fake, nullptr, nullptr, cprob, Bi, Bi, Bi, 1, 1, acc};
+  if (tc_ok) {
+    // The martingale adjoint (a few MFLOP, ~10 us of latency) and the gradient GEMM both depend on Cbar3
+    // only: the small kernel goes first on the side stream and the persistent GEMM CTAs fill in around it.
+    SideLane* lane = side_lane();
+    cudaStream_t ms = st;
+    if (lane) {
+      KCCOT_CUDA(cudaEventRecord(lane->fork, st));
+      KCCOT_CUDA(cudaStreamWaitEvent(lane->stream, lane->fork, 0));
+      ms = lane->stream;
+    }
+    if (int rc = launch_martingale_jobs(jobs, 4, nprob, T, J, s, ms)) return rc;
+    if (lane) KCCOT_CUDA(cudaEventRecord(lane->join, lane->stream));
+    if (int rc = launch_grad_tc(Cbar3, real, fake, nprob, B, B, K, s, g_real, g_fake, acc, (float*)ws, st)) return rc;
+    if (lane) KCCOT_CUDA(cudaStreamWaitEvent(st, lane->join, 0));
+    return KCCOT_OK;
+  }
+  if (g_fake) {
+    if (int rc = launch_cost_bwd_simt(Cxy, 1, B, cprob, fake, real, nprob, B, B, K, s, g_fake, acc, st)) return rc;
+    if (int rc = launch_cost_bwd_simt(Cyy, B, 1, cprob, fake, fake, nprob, B, B, K, s, g_fake, 1, st)) return rc;
+    if (int rc = launch_cost_bwd_simt(Cyy, 1, B, cprob, fake, fake, nprob, B, B, K, s, g_fake, 1, st)) return rc;
+  }
+  if (g_real) {
+    if (int rc = launch_cost_bwd_simt(Cxy, B, 1, cprob, real, fake, nprob, B, B, K, s, g_real, acc, st)) return rc;
+    if (int rc = launch_cost_bwd_simt(Cxx, B, 1, cprob, real, real, nprob, B, B, K, s, g_real, 1, st)) return rc;
+    if (int rc = launch_cost_bwd_simt(Cxx, 1, B, cprob, real, real, nprob, B, B, K, s, g_real, 1, st)) return rc;
+  }
   if (int rc = launch_martingale_jobs(jobs, 4, nprob, T, J, s, st)) return rc;
   return KCCOT_OK;
 }

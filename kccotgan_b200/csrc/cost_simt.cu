@@ -92,52 +92,95 @@ void choose_ksplit_simt(int nprob, int Bx, int By, long long K, int* ksplit, lon
 
 // ---------------------------------------------------------------------------------------------
 // C = s * sum_ks P + s * sum_pairs h_row . DeltaM_col
+//
+// One CTA = one 8 x 8 tile of one output block (and, for `sym` partials, its mirror tile), G k-slab
+// groups of 128 threads.  Within a group 64 threads read the tile as stored and 64 read the mirror
+// tile, eight consecutive floats (one 32-byte sector) per row, so every sector fetched from L2 is
+// fully used although k-slabs are 64 KB apart.  `sym` partials (tensor-core path) hold
+// P'_ij = n_i + n_j - 2 (H_ij + 2 X_ij) with X = hi lo^T only: the missing lo hi^T = X^T comes back as
+// C_ij = (P'_ij + P'_ji) / 2.  The split-K partials are summed in fp64: a sequential fp32 sum of
+// ~150-300 partials of a value near 1e4 would by itself cost ~5e-4 absolute on C, more than the whole
+// fp32 budget of the path.
 // ---------------------------------------------------------------------------------------------
-constexpr int FL = 8;   // lanes cooperating on one output element
+constexpr int FT = 8;     // tile edge
+constexpr int FGmax = 8;  // k-slab groups per CTA
 
-__global__ void __launch_bounds__(256) cost_finalize_kernel(CostBlocks blocks, int nprob, int T, int J,
-                                                            float s) {
+__global__ void __launch_bounds__(128 * FGmax) cost_finalize_kernel(CostBlocks blocks, int T, int J, float s) {
+  __shared__ double red[FGmax][2][FT * FT];
   const CostBlock& b = blocks.b[blockIdx.z];
-  const long long n = (long long)nprob * b.Bx * b.By;
-  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long idx = gid / FL;
-  const int sub = (int)(gid % FL);
-  const bool live = idx < n;
-  const int j = live ? (int)(idx % b.By) : 0;
-  const int i = live ? (int)((idx / b.By) % b.Bx) : 0;
-  const int p = live ? (int)(idx / ((long long)b.Bx * b.By)) : 0;
-  // the split-K partials are summed in fp64: a sequential fp32 sum of ~150-300 partials of a value
-  // near 1e4 would by itself cost ~5e-4 absolute on C, more than the whole fp32 budget of the path
+  const int tiles_j = (b.By + FT - 1) / FT, tiles_i = (b.Bx + FT - 1) / FT;
+  if ((int)blockIdx.x >= tiles_i * tiles_j) return;
+  const int p = blockIdx.y;
+  const int ti = blockIdx.x / tiles_j, tj = blockIdx.x % tiles_j;
+  const int G = blockDim.x >> 7;
+  const int tid = threadIdx.x, g = tid >> 7, mirror = (tid >> 6) & 1, r = (tid >> 3) & 7, c = tid & 7;
+  // the output element this thread contributes to
+  const int ei = ti * FT + (mirror ? c : r), ej = tj * FT + (mirror ? r : c);
+  const bool live = ei < b.Bx && ej < b.By;
   double d = 0.0;
-  if (live && !(b.zero_diag && i == j)) {
-    const float* pp = b.part + (long long)p * b.prob_stride + (long long)(b.row_off + i) * b.ld + b.col_off + j;
-    for (int ks = sub; ks < b.nks; ks += FL) d += (double)pp[(long long)ks * b.ks_stride];
+  if (live && !(b.zero_diag && ei == ej) && (!mirror || b.sym)) {
+    const float* pp = b.part + (long long)p * b.prob_stride +
+                      (mirror ? (long long)(b.col_off + ej) * b.ld + b.row_off + ei
+                              : (long long)(b.row_off + ei) * b.ld + b.col_off + ej);
+    constexpr int kBatch = 8;
+    for (int ks0 = g; ks0 < b.nks; ks0 += G * kBatch) {
+      float v[kBatch];
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u) {
+        const int ks = ks0 + u * G;
+        v[u] = (ks < b.nks) ? pp[(long long)ks * b.ks_stride] : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u) d += (double)v[u];
+    }
+    if (b.sym) d *= 0.5;
   }
-  const int tj = (T - 1) * J;
+  const int tj1 = (T - 1) * J;
   float a = 0.f;
   if (live) {
     for (int pair = 0; pair < 2; ++pair) {
       const float* h = pair ? b.h2 : b.h1;
       const float* M = pair ? b.M2 : b.M1;
       if (h == nullptr) continue;
-      const float* hr = h + ((long long)p * b.Bx + i) * T * J;
-      const float* Mr = M + ((long long)p * b.By + j) * T * J;
-      for (int q = sub; q < tj; q += FL) a = fmaf(hr[q], Mr[q + J] - Mr[q], a);
+      const float* hr = h + ((long long)p * b.Bx + ei) * T * J;
+      const float* Mr = M + ((long long)p * b.By + ej) * T * J;
+      for (int q = g * 2 + mirror; q < tj1; q += 2 * G) a = fmaf(hr[q], Mr[q + J] - Mr[q], a);
     }
   }
-  d += (double)a;
-#pragma unroll
-  for (int o = FL / 2; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
-  if (live && sub == 0) b.C[(long long)p * b.C_prob_stride + (long long)i * b.By + j] = (float)((double)s * d);
+  red[g][mirror][mirror ? c * FT + r : r * FT + c] = d + (double)a;
+  __syncthreads();
+  if (tid < FT * FT) {
+    const int oi = ti * FT + (tid >> 3), oj = tj * FT + (tid & 7);
+    if (oi < b.Bx && oj < b.By) {
+      double t = 0.0;
+      for (int gg = 0; gg < G; ++gg) t += red[gg][0][tid] + red[gg][1][tid];      // fixed order: deterministic
+      b.C[(long long)p * b.C_prob_stride + (long long)oi * b.By + oj] = (float)((double)s * t);
+    }
+  }
 }
 
 int launch_cost_finalize(const CostBlocks& blocks, int nblocks, int nprob, int T, int J, float s,
                          cudaStream_t st) {
-  long long nmax = 0;
-  for (int i = 0; i < nblocks; ++i) nmax = max(nmax, (long long)nprob * blocks.b[i].Bx * blocks.b[i].By);
-  dim3 grid((unsigned)((nmax * FL + 255) / 256), 1, nblocks);
-  cost_finalize_kernel<<<grid, 256, 0, st>>>(blocks, nprob, T, J, s);
-  KCCOT_LAUNCH_CHECK();
+  int tiles = 0, nks = 1;
+  for (int i = 0; i < nblocks; ++i) {
+    const CostBlock& b = blocks.b[i];
+    tiles = max(tiles, ((b.Bx + FT - 1) / FT) * ((b.By + FT - 1) / FT));
+    nks = max(nks, b.nks);
+  }
+  const int G = nks >= 64 ? 8 : nks >= 16 ? 4 : nks >= 4 ? 2 : 1;
+  for (int p0 = 0; p0 < nprob; p0 += 65535) {     // grid.y limit
+    CostBlocks bl = blocks;
+    const int np = min(65535, nprob - p0);
+    for (int i = 0; i < nblocks; ++i) {
+      bl.b[i].part += (long long)p0 * bl.b[i].prob_stride;
+      bl.b[i].C += (long long)p0 * bl.b[i].C_prob_stride;
+      if (bl.b[i].h1) { bl.b[i].h1 += (long long)p0 * bl.b[i].Bx * T * J; bl.b[i].M1 += (long long)p0 * bl.b[i].By * T * J; }
+      if (bl.b[i].h2) { bl.b[i].h2 += (long long)p0 * bl.b[i].Bx * T * J; bl.b[i].M2 += (long long)p0 * bl.b[i].By * T * J; }
+    }
+    dim3 grid((unsigned)tiles, (unsigned)np, (unsigned)nblocks);
+    cost_finalize_kernel<<<grid, 128 * G, 0, st>>>(bl, T, J, s);
+    KCCOT_LAUNCH_CHECK();
+  }
   return KCCOT_OK;
 }
 

@@ -9,14 +9,17 @@
 //                    accumulate the fp32 row norms, split into tf32 hi + tf32 lo in place.  Warp w
 //                    owns 16-byte chunk w of all 128 rows, so the column mean is a warp-shuffle
 //                    reduction and the only shared-memory traffic is tile in (16 KB) + hi/lo out (32 KB).
-//   MMA thread    : D += hi.hi^T + hi.lo^T + lo.hi^T   (3xTF32, fp32 accumulate in TMEM).  The tensor
+//   MMA thread    : H += hi.hi^T, X += hi.lo^T   (3xTF32 with the third product lo.hi^T = X^T recovered by
+//                    symmetry: the partial tile carries 2X and cost_finalize_kernel averages it with its
+//                    transpose; 8 instead of 12 MMAs per k-block; fp32 accumulate in TMEM).  The tensor
 //                    core's fp32 accumulation truncates, so a long chain into one large accumulator
 //                    (e.g. D_ii ~ |x_i|^2 for a fake that resembles its real) picks up a bias that grows
 //                    with chain length x magnitude.  The hi.hi products are therefore dealt round-robin
 //                    to three TMEM accumulators and the (2^-11 smaller) cross products go to a fourth;
 //                    the epilogue adds the four in fp32 (measured: 9x smaller error on video-like data).
-//   epilogue      : P_ij = n_i + n_j - 2 D_ij  ->  part[p][ks][128][128]  (partial squared distances;
-//                    cost_finalize_kernel sums the slabs and adds the martingale terms).
+//   epilogue      : P'_ij = n_i + n_j - 2 (H_ij + 2 X_ij)  ->  part[p][ks][128][128]  (partial squared
+//                    distances up to the symmetrisation; cost_finalize_kernel sums the slabs in fp64,
+//                    forms (P'_ij + P'_ji) / 2 and adds the martingale terms).
 #include "cost.cuh"
 #include "tc_common.cuh"
 
@@ -100,7 +103,7 @@ sqdist_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
     }
   } else if (warp == 1) {
     // ------------------------------- MMA issuer -----------------------------------------------
-    {   // the whole warp runs this loop with uniform operands; one elected lane issues each instruction
+    if (tc::elect_one()) {
       const uint32_t idesc = tc::make_idesc_tf32(128, N, 0, 0);
       int stage = 0, phase = 0, acc_phase = 0;
       for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
@@ -118,12 +121,11 @@ sqdist_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
             const uint64_t dh = tc::make_smem_desc_sw128(hi_addr + k4 * 32, 16, 1024);
             const uint64_t dl = tc::make_smem_desc_sw128(lo_addr + k4 * 32, 16, 1024);
             const int step = (kb - kb0) * (kKB / 8) + k4;
-            tc::umma_tf32_warp(tmem + (uint32_t)((step % 3) * kRows), dh, dh, idesc, step >= 3 ? 1u : 0u);
-            tc::umma_tf32_warp(tmem + (uint32_t)(3 * kRows), dh, dl, idesc, step > 0 ? 1u : 0u);
-            tc::umma_tf32_warp(tmem + (uint32_t)(3 * kRows), dl, dh, idesc, 1u);
+            tc::umma_tf32(tmem + (uint32_t)((step % 3) * kRows), dh, dh, idesc, step >= 3 ? 1u : 0u);
+            tc::umma_tf32(tmem + (uint32_t)(3 * kRows), dh, dl, idesc, step > 0 ? 1u : 0u);
           }
-          tc::umma_commit_warp(&S.empty[stage]);
-          if (kb == kb1 - 1) tc::umma_commit_warp(&S.acc_full);
+          tc::umma_commit(&S.empty[stage]);
+          if (kb == kb1 - 1) tc::umma_commit(&S.acc_full);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
         acc_phase ^= 1;
@@ -220,8 +222,9 @@ sqdist_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
             float t[32];
             tc::tmem_ld_32x32(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(a * kRows + c0), t);
             tc::tmem_ld_wait();
+            const float wt = (a == kNumAcc - 1) ? 2.f : 1.f;          // X stands for X + X^T (see finalize)
 #pragma unroll
-            for (int j = 0; j < 32; ++j) d[j] += t[j];
+            for (int j = 0; j < 32; ++j) d[j] = fmaf(wt, t[j], d[j]);
           }
           if (row < R) {
 #pragma unroll

@@ -22,23 +22,10 @@
 // back one iteration and continues, for the rest of the solve, with the plain log-domain updates with
 // max subtraction — the reference's formulation.  The backward switches to direct exponentials before
 // any rank-one factor would leave 2^+-60.
-#include <type_traits>
-
 #include "common.cuh"
 #include "sinkhorn.cuh"
 
 namespace kccot {
-
-// Development-only phase timeline (build with -DKCCOT_SK_TRACE; scripts/sk_trace.py reads it).
-#ifdef KCCOT_SK_TRACE
-__device__ long long g_sk_trace[2][16];
-#define SK_STAMP(kern, idx)                                                          \
-  do {                                                                               \
-    if (blockIdx.x == 0 && threadIdx.x == 0) g_sk_trace[kern][idx] = clock64();      \
-  } while (0)
-#else
-#define SK_STAMP(kern, idx)
-#endif
 
 namespace {
 constexpr float kBig = 1e30f;      // padding cost: exp2(anything - kBig) == 0, and 0 * kBig == 0
@@ -127,36 +114,6 @@ __device__ __forceinline__ float lse_update(const float (&Cs)[EPT], const float*
 template <int EPT>
 __device__ __forceinline__ int pad_index(int j) { return (j / EPT) * (EPT + 4) + (j % EPT); }
 
-// Pins a shared-window address in a register.  Without this ptxas rematerialises the address inside
-// the iteration loop from S2R SR_CgaCtaId, whose latency (~200 cycles) then sits in front of the
-// mat-vec's loads every half-iteration (measured: 390 -> 510 ns per iteration).
-__device__ __forceinline__ uint32_t pin_u32(uint32_t v) {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v));
-  return r;
-}
-
-__device__ __forceinline__ int lds_flag(uint32_t saddr) {
-  int v;
-  asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"(saddr) : "memory");
-  return v;
-}
-__device__ __forceinline__ void sts_flag(uint32_t saddr, int v) {
-  asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
-}
-
-__device__ __forceinline__ void sts128(uint32_t saddr, float4 v) {
-  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-}
-__device__ __forceinline__ float lds_f32(uint32_t saddr) {
-  float v;
-  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr) : "memory");
-  return v;
-}
-__device__ __forceinline__ void sts_f32(uint32_t saddr, float v) {
-  asm volatile("st.shared.f32 [%0], %1;" ::"r"(saddr), "f"(v) : "memory");
-}
-
 __device__ __forceinline__ float4 lds128(uint32_t saddr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
@@ -195,6 +152,7 @@ __global__ void __launch_bounds__(4 * 4 * EPT) sinkhorn_fwd_small_kernel(
   __shared__ __align__(16) float as[BMP], bs[BMP];      // linear scalings a_i, b_j of the fast path (padded)
   __shared__ float red[32];
   __shared__ int stop_flag, bad_flag;
+  __shared__ volatile int chg;
   const int n = blockIdx.x;
   const int tid = threadIdx.x, i = tid >> 2, q = tid & 3;
   const int ic = min(i, BM - 1);
@@ -203,9 +161,7 @@ __global__ void __launch_bounds__(4 * 4 * EPT) sinkhorn_fwd_small_kernel(
   const float ahat = -log2f((float)B);
   const float two_ahat = 1.f / (float)B;
   float Cr[EPT], Cc[EPT], Kr[EPT], Kc[EPT];
-  SK_STAMP(0, 0);
   const float c0 = load_slices<EPT>(C + (long long)n * B * B, B, kscale, red, Cr, Cc);
-  SK_STAMP(0, 1);
   float* uh = u_hist + (long long)n * (L + 1) * B;
   float* vh = v_hist + (long long)n * (L + 1) * B;
   float* Uh = hist;
@@ -223,14 +179,12 @@ __global__ void __launch_bounds__(4 * 4 * EPT) sinkhorn_fwd_small_kernel(
     alpha = quad_min(rm);
   }
   const int ip = pad_index<EPT>(ic);                            // padded slot of row / column i
-  const uint32_t as_q = pin_u32(static_cast<uint32_t>(__cvta_generic_to_shared(as)) + q * (EPT + 4) * 4);
-  const uint32_t bs_q = pin_u32(static_cast<uint32_t>(__cvta_generic_to_shared(bs)) + q * (EPT + 4) * 4);
-  const uint32_t bad_a = pin_u32(static_cast<uint32_t>(__cvta_generic_to_shared(&bad_flag)));
-  const uint32_t bs_i = pin_u32(static_cast<uint32_t>(__cvta_generic_to_shared(&bs[ip])));
+  const uint32_t as_q = static_cast<uint32_t>(__cvta_generic_to_shared(as)) + q * (EPT + 4) * 4;
+  const uint32_t bs_q = static_cast<uint32_t>(__cvta_generic_to_shared(bs)) + q * (EPT + 4) * 4;
   for (int t = tid; t < BM; t += blockDim.x) { urow(0)[t] = 0.f; vrow(0)[t] = 0.f; }
   for (int t = tid; t < BMP; t += blockDim.x) { as[t] = 0.f; bs[t] = 0.f; }
   if (!HS && tid < B) { uh[tid] = 0.f; vh[tid] = 0.f; }
-  if (tid == 0) { stop_flag = 0; bad_flag = 0; }
+  if (tid == 0) { stop_flag = 0; bad_flag = 0; chg = -2; }
   __syncthreads();
   if (owner) { as[ip] = alpha; bs[ip] = 1.f; }   // stage the row minima for the column slices; b = exp2(0)
   __syncthreads();
@@ -245,7 +199,6 @@ __global__ void __launch_bounds__(4 * 4 * EPT) sinkhorn_fwd_small_kernel(
 
   const float ahat_alpha = ahat + alpha;
   float u_cur = 0.f;            // uhat of this thread's row (all four lanes of a row hold it)
-  SK_STAMP(0, 2);
   bool slow = false;
   int it = 0, nits = 0;
   // iterations before `first_check` can never stop (gan_utils.py:159 needs nits >= Lmin, :116 needs the
@@ -256,61 +209,33 @@ __global__ void __launch_bounds__(4 * 4 * EPT) sinkhorn_fwd_small_kernel(
       // Fixed-point short cut: the iteration is a deterministic function of the column scalings b, so
       // once an iteration returns b bit-for-bit (fp32 Sinkhorn does: after 1 iteration on the
       // diagonal-dominant xx / yy problems, after 55-70 on cfg2's uniform xy problem) every later
-      // iteration reproduces the same potentials; the remaining history rows are copies.  Only every
-      // 8th iteration carries the test (a reducing barrier in place of the plain one); the other seven
-      // run in an inner loop with nothing but the two mat-vecs between barriers (a per-iteration test,
-      // even off the critical path, cost 65-120 ns of the ~390 ns iteration in control instructions).
-      // Returns 0: done, 1: guard flag seen (nothing written), 2: fixed point reached.
-      float unew = 0.f, vnew = 0.f;
-      auto iteration = [&](auto check_tag) -> int {
-        constexpr bool kCheck = decltype(check_tag)::value;
+      // iteration reproduces the same potentials; the remaining history rows are copies.  Threads whose
+      // b changed stamp the iteration number into `chg`; the stamp is read one iteration later, off
+      // the critical path (a barrier-with-reduction every iteration cost ~110 ns of the ~450).
+      float b_prev = __int_as_float(0x7fc00000);
+      for (; it < first_check; ++it) {
         const float s = dot_slice<EPT>(Kr, bs_q);
-        if (lds_flag(bad_a)) return 1;                    // set during iteration it-1: rolled back below
+        if (bad_flag) break;                              // set during iteration it-1: rolled back below
         const float a_new = two_ahat * fast_rcp(s);       // critical path first
-        unew = ahat + alpha - fast_log2(s);
+        const float unew = ahat + alpha - fast_log2(s);
         if (owner) {
           as[ip] = a_new;
           urow(it + 1)[i] = unew;
           if (!HS) uh[(long long)(it + 1) * B + i] = unew;
-          if (!(s > kLo && s < kHi)) sts_flag(bad_a, 1);
+          if (!(s > kLo && s < kHi)) bad_flag = 1;
         }
         __syncthreads();
         const float t = dot_slice<EPT>(Kc, as_q);
         const float b_new = two_ahat * fast_rcp(t);
-        vnew = ahat - fast_log2(t);
-        float b_old = 0.f;
-        if (kCheck) b_old = lds_f32(bs_i);                // previous b (read before the owner lane's store)
+        const float vnew = ahat - fast_log2(t);
         if (owner) {
           bs[ip] = b_new;
           vrow(it + 1)[i] = vnew;
           if (!HS) vh[(long long)(it + 1) * B + i] = vnew;
-          if (!(t > kLo && t < kHi)) sts_flag(bad_a, 1);
+          if (!(t > kLo && t < kHi)) bad_flag = 1;
         }
-        if (!kCheck) {
-          __syncthreads();
-          return 0;
-        }
-        const int fixed = __syncthreads_and((i >= B) | (b_new == b_old));
-        return (fixed && lds_flag(bad_a) == 0) ? 2 : 0;
-      };
-      bool leave = false;
-      while (it < first_check && !leave) {
-        const int plain_end = it + min(first_check - it, 8) - 1;
-        for (; it < plain_end; ++it)
-          if (iteration(std::false_type{})) { leave = true; break; }
-        if (leave) break;
-        const int rc = iteration(std::true_type{});
-        if (rc == 1) break;
-        if (rc == 2) {                                    // rows >= it + 1 are all equal
-          if (owner)
-            for (int r = it + 2; r <= first_check; ++r) {
-              if (HS) { urow(r)[i] = unew; vrow(r)[i] = vnew; }
-              else { uh[(long long)r * B + i] = unew; vh[(long long)r * B + i] = vnew; }
-            }
-          it = first_check;
-          break;
-        }
-        ++it;
+        b_prev = b_new;
+        __syncthreads();
       }
       nits = it;
       if (bad_flag) {                                     // iteration it-1 left the safe range: redo it in the log domain
@@ -406,7 +331,6 @@ __global__ void __launch_bounds__(4 * 4 * EPT) sinkhorn_fwd_small_kernel(
     }
     break;
   }
-  SK_STAMP(0, 3);
   // ---- sharp cost sum(pi * C) ---------------------------------------------------------------
   float s1 = 0.f, s0 = 0.f;
   {
@@ -425,30 +349,13 @@ __global__ void __launch_bounds__(4 * 4 * EPT) sinkhorn_fwd_small_kernel(
     cost_out[n] = s1 / kscale + c0 * s0;
     nits_out[n] = nits;
   }
-  SK_STAMP(0, 4);
   if (HS) {
-    const int total = (nits + 1) * B;
-    if (B == BM && ((reinterpret_cast<uintptr_t>(uh) | reinterpret_cast<uintptr_t>(vh)) & 15) == 0) {
-      // rows are contiguous in both places: a straight 16-byte copy, no index arithmetic
-      const float4* U4 = reinterpret_cast<const float4*>(Uh);
-      const float4* V4 = reinterpret_cast<const float4*>(Vh);
-      float4* u4 = reinterpret_cast<float4*>(uh);
-      float4* v4 = reinterpret_cast<float4*>(vh);
-      for (int f = tid; f < (total >> 2); f += blockDim.x) {
-        u4[f] = U4[f];
-        v4[f] = V4[f];
-      }
-    } else {
-      for (int k = tid / BM; k <= nits; k += blockDim.x / BM) {
-        const int j = tid % BM;
-        if (j < B) {
-          uh[(long long)k * B + j] = Uh[(size_t)k * BM + j];
-          vh[(long long)k * B + j] = Vh[(size_t)k * BM + j];
-        }
-      }
+    for (int e = tid; e < (nits + 1) * B; e += blockDim.x) {
+      const int k = e / B, j = e % B;
+      uh[e] = Uh[(size_t)k * BM + j];
+      vh[e] = Vh[(size_t)k * BM + j];
     }
   }
-  SK_STAMP(0, 5);
 }
 
 // HS = true: the whole potential history (nits+1 rows of u and v) is copied to shared memory up
@@ -479,9 +386,7 @@ __global__ void __launch_bounds__(4 * 4 * EPT) sinkhorn_bwd_small_kernel(
   const float kscale = kLog2e / eps;
   const float ahat = -log2f((float)B);
   float Cr[EPT], Cc[EPT], Kr[EPT], Kc[EPT], Gr[EPT], Gc[EPT];
-  SK_STAMP(1, 0);
   load_slices<EPT>(C + (long long)n * B * B, B, kscale, red, Cr, Cc);
-  SK_STAMP(1, 1);
   const float* uh = u_hist + (long long)n * (L + 1) * B;
   const float* vh = v_hist + (long long)n * (L + 1) * B;
   const int nits = nits_in[n];
@@ -500,7 +405,6 @@ __global__ void __launch_bounds__(4 * 4 * EPT) sinkhorn_bwd_small_kernel(
     vn_s[tp] = vh[(long long)nits * B + tid];
   }
   __syncthreads();
-  SK_STAMP(1, 2);
   if (HS) {
     // copy the history; remember the last step whose potentials are further than 2^60 from the
     // absorption reference (steps k <= k_slow + 1 use direct exponentials).  All loads of a thread are
@@ -515,11 +419,7 @@ __global__ void __launch_bounds__(4 * 4 * EPT) sinkhorn_bwd_small_kernel(
     if ((B & 3) == 0 && ((reinterpret_cast<uintptr_t>(uh) | reinterpret_cast<uintptr_t>(vh)) & 15) == 0) {
       const float4* u4 = reinterpret_cast<const float4*>(uh);
       const float4* v4 = reinterpret_cast<const float4*>(vh);
-      auto sa = [](const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); };
-      const uint32_t un_a = pin_u32(sa(un_s)), vn_a = pin_u32(sa(vn_s));
-      const uint32_t U_a = pin_u32(sa(Uh)), V_a = pin_u32(sa(Vh));
-      const int B4 = B >> 2;
-      constexpr int kBatch = 8;
+      constexpr int kBatch = 4;
       for (int f0 = tid; f0 < (total >> 2); f0 += blockDim.x * kBatch) {
         float4 u[kBatch], v[kBatch];
 #pragma unroll
@@ -531,17 +431,17 @@ __global__ void __launch_bounds__(4 * 4 * EPT) sinkhorn_bwd_small_kernel(
         for (int t = 0; t < kBatch; ++t) {
           const int f = f0 + t * blockDim.x;
           if (f < (total >> 2)) {
-            const int k = f / B4, j = (f - k * B4) << 2;
-            const uint32_t jp = (uint32_t)pad_index<EPT>(j) * 4;   // 4 consecutive columns stay inside one chunk
-            const float4 ru = lds128(un_a + jp);
-            const float4 rv = lds128(vn_a + jp);
+            const int k = (4 * f) / B, j = (4 * f) - k * B;
+            const int jp = pad_index<EPT>(j);               // 4 consecutive columns stay inside one chunk
+            const float4 ru = *reinterpret_cast<const float4*>(&un_s[jp]);
+            const float4 rv = *reinterpret_cast<const float4*>(&vn_s[jp]);
             const bool ok = fabsf(u[t].x - ru.x) <= kExpLim && fabsf(u[t].y - ru.y) <= kExpLim &&
                             fabsf(u[t].z - ru.z) <= kExpLim && fabsf(u[t].w - ru.w) <= kExpLim &&
                             fabsf(v[t].x - rv.x) <= kExpLim && fabsf(v[t].y - rv.y) <= kExpLim &&
                             fabsf(v[t].z - rv.z) <= kExpLim && fabsf(v[t].w - rv.w) <= kExpLim;
             if (!ok) kmax = max(kmax, k);
-            sts128(U_a + (uint32_t)k * (BMP * 4) + jp, u[t]);
-            sts128(V_a + (uint32_t)k * (BMP * 4) + jp, v[t]);
+            *reinterpret_cast<float4*>(&Uh[(size_t)k * BMP + jp]) = u[t];
+            *reinterpret_cast<float4*>(&Vh[(size_t)k * BMP + jp]) = v[t];
           }
         }
       }
@@ -578,7 +478,6 @@ __global__ void __launch_bounds__(4 * 4 * EPT) sinkhorn_bwd_small_kernel(
     }
   }
   __syncthreads();
-  SK_STAMP(1, 3);
   const float un_i = un_s[ip], vn_i = vn_s[ip];    // row i / column i of this thread
   // ---- adjoint seeds.  cost = sum(pi*C) = sum(pi*(C - c0)) + c0*sum(pi), and sum(pi) == 1 identically
   // in the inputs (the last v-update normalises every column of pi to 1/B), so the c0 term has zero
@@ -606,71 +505,12 @@ __global__ void __launch_bounds__(4 * 4 * EPT) sinkhorn_bwd_small_kernel(
     }
   }
   __syncthreads();
-  const uint32_t ga_q = pin_u32(static_cast<uint32_t>(__cvta_generic_to_shared(ga)) + qo * 4);
-  const uint32_t gb_q = pin_u32(static_cast<uint32_t>(__cvta_generic_to_shared(gb)) + qo * 4);
+  const uint32_t ga_q = static_cast<uint32_t>(__cvta_generic_to_shared(ga)) + qo * 4;
+  const uint32_t gb_q = static_cast<uint32_t>(__cvta_generic_to_shared(gb)) + qo * 4;
   const int kslow = HS ? k_slow : -1;
-  // pinned shared-window addresses of this thread's elements (see pin_u32)
-  auto sa = [](const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); };
-  const uint32_t ub_i = pin_u32(sa(&ub[ip])), vb_i = pin_u32(sa(&vb[ip]));
-  const uint32_t ga_i = pin_u32(sa(&ga[ip])), gb_i = pin_u32(sa(&gb[ip]));
-  const uint32_t Uh_i = pin_u32(sa(HS ? &Uh[ip] : &Us[0][ip])), Vh_i = pin_u32(sa(HS ? &Vh[ip] : &Vs[0][ip]));
 
-  SK_STAMP(1, 4);
-  int k = nits;
-  if (HS) {
-    // ---- fast steps (all potentials within 2^60 of the absorption reference): a loop with nothing but
-    // the two mat-vecs, the rank-one accumulation and two barriers; every branch removed from it was
-    // worth 10-20 ns of the ~420 ns step (single-warp-per-scheduler latency, see the forward kernel).
-    float ub_carry = owner ? lds_f32(ub_i) : 0.f;        // the seed enters the first step only
-    const uint32_t step_bytes = BMP * 4;
-    uint32_t u_a = Uh_i + (uint32_t)k * step_bytes, v_a = Vh_i + (uint32_t)(k - 1) * step_bytes;
-    for (; k >= max(kslow + 2, 1); --k, u_a -= step_bytes, v_a -= step_bytes) {
-      const float uk_i = lds_f32(u_a);
-      const float fa = fast_exp2(uk_i - un_i);
-      float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-      for (int e = 0; e < EPT; e += 4) {
-        const float4 w = lds128(gb_q + e * 4);
-        const float t0 = Kr[e] * w.x, t1 = Kr[e + 1] * w.y, t2 = Kr[e + 2] * w.z, t3 = Kr[e + 3] * w.w;
-        Gr[e] = fmaf(t0, fa, Gr[e]);
-        Gr[e + 1] = fmaf(t1, fa, Gr[e + 1]);
-        Gr[e + 2] = fmaf(t2, fa, Gr[e + 2]);
-        Gr[e + 3] = fmaf(t3, fa, Gr[e + 3]);
-        a0 += t0 + t2;
-        a1 += t1 + t3;
-      }
-      const float ubn = ub_carry - quad_sum((a0 + a1) * fa);
-      ub_carry = 0.f;
-      if (owner) {
-        sts_f32(ub_i, ubn);
-        sts_f32(ga_i, fa * ubn);                          // |u^k - u^n| <= 2^60 here: no clamp needed
-      }
-      __syncthreads();
-      const float vkm1_j = lds_f32(v_a);
-      const float fb = fast_exp2(vkm1_j - vn_i - ahat);
-      float c0 = 0.f, c1 = 0.f;
-#pragma unroll
-      for (int e = 0; e < EPT; e += 4) {
-        const float4 w = lds128(ga_q + e * 4);
-        const float t0 = Kc[e] * w.x, t1 = Kc[e + 1] * w.y, t2 = Kc[e + 2] * w.z, t3 = Kc[e + 3] * w.w;
-        Gc[e] = fmaf(t0, fb, Gc[e]);
-        Gc[e + 1] = fmaf(t1, fb, Gc[e + 1]);
-        Gc[e + 2] = fmaf(t2, fb, Gc[e + 2]);
-        Gc[e + 3] = fmaf(t3, fb, Gc[e + 3]);
-        c0 += t0 + t2;
-        c1 += t1 + t3;
-      }
-      const float vbn = -quad_sum((c0 + c1) * fb);
-      if (owner) {
-        sts_f32(vb_i, vbn);
-        sts_f32(gb_i, fb * vbn);
-      }
-      __syncthreads();
-    }
-  }
-  SK_STAMP(1, 5);
   bool slow = false;
-  for (; k >= 1; --k) {
+  for (int k = nits; k >= 1; --k) {
     const int b = k & 1;
     const float* Uk = HS ? Uh + (size_t)k * BMP : Us[b];
     const float* Vk = HS ? Vh + (size_t)k * BMP : Vs[b];
@@ -686,7 +526,7 @@ __global__ void __launch_bounds__(4 * 4 * EPT) sinkhorn_bwd_small_kernel(
     // ---- through v^k = a - eps*LSE_i((u^k_i - C_ij)/eps):  Pv_ij = exp((u^k_i + v^k_j - a - C_ij)/eps)
     //      Cbar += Pv * vbar_j ;  ubar_i = (k == nits ? ubar_i : 0) - sum_j Pv_ij vbar_j
     {
-      const float uk_i = lds_f32(Uh_i + (HS ? k : b) * (BMP * 4));
+      const float uk_i = Uk[ip];
       float part;
       if (!slow) {
         // Pv_ij vbar_j = pi_ij * exp2(u^k_i - u^n_i) * gb_j
@@ -717,9 +557,9 @@ __global__ void __launch_bounds__(4 * 4 * EPT) sinkhorn_bwd_small_kernel(
       }
       const float acc = quad_sum(part);
       if (owner) {
-        const float ubn = ((k == nits) ? lds_f32(ub_i) : 0.f) - acc;
-        sts_f32(ub_i, ubn);
-        sts_f32(ga_i, fast_exp2(fminf(fmaxf(uk_i - un_i, -kExpLim), kExpLim)) * ubn);   // for the column phase
+        const float ubn = ((k == nits) ? ub[ip] : 0.f) - acc;
+        ub[ip] = ubn;
+        ga[ip] = fast_exp2(fminf(fmaxf(uk_i - un_i, -kExpLim), kExpLim)) * ubn;   // for the column phase
       }
     }
     __syncthreads();
@@ -727,7 +567,7 @@ __global__ void __launch_bounds__(4 * 4 * EPT) sinkhorn_bwd_small_kernel(
     // ---- through u^k = a - eps*LSE_j((v^{k-1}_j - C_ij)/eps):  Pu_ij = exp((u^k_i + v^{k-1}_j - a - C_ij)/eps)
     //      Cbar += Pu * ubar_i ;  vbar_j = - sum_i Pu_ij ubar_i
     {
-      const float vkm1_j = lds_f32(Vh_i + (HS ? k - 1 : (b ^ 1)) * (BMP * 4));
+      const float vkm1_j = Vkm1[ip];
       const float fb = fast_exp2(fminf(fmaxf(vkm1_j - vn_i, -kExpLim), kExpLim) - ahat);
       float part;
       if (!slow) {
@@ -757,8 +597,8 @@ __global__ void __launch_bounds__(4 * 4 * EPT) sinkhorn_bwd_small_kernel(
       }
       const float acc = quad_sum(part);
       if (owner) {
-        sts_f32(vb_i, -acc);
-        sts_f32(gb_i, fb * (-acc));          // factor of the next row phase: v^{k-1} here is its v^k
+        vb[ip] = -acc;
+        gb[ip] = fb * (-acc);          // factor of the next row phase: v^{k-1} here is its v^k
       }
       if (!HS && tid < B && k >= 2) {
         Us[b ^ 1][tp] = pu;     // u^{k-1}
@@ -769,50 +609,23 @@ __global__ void __launch_bounds__(4 * 4 * EPT) sinkhorn_bwd_small_kernel(
     }
     __syncthreads();
   }
-  SK_STAMP(1, 6);
   // ---- Cbar = g * (Gr + Gc^T) ---------------------------------------------------------------
   float* out = Cbar + (long long)n * B * B;
-  if (HS) {
-    // transpose the column-slice accumulators through shared memory (the history is dead) and write
-    // every row once, 16 bytes at a time (the read-modify-write through global memory took 2.9 us)
-    constexpr int TS = BM + 1;
-    float* T = hist;                                      // launcher guarantees BM * TS floats
+  if (i < B) {
 #pragma unroll
-    for (int e = 0; e < EPT; ++e) T[(q * EPT + e) * TS + min(i, BM - 1)] = Gc[e];
-    __syncthreads();
-    if (i < B) {
-      float o[EPT];
-#pragma unroll
-      for (int e = 0; e < EPT; ++e) o[e] = g * (Gr[e] + T[i * TS + q * EPT + e]);
-      float* dst = out + (long long)i * B + q * EPT;
-      if ((B & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
-#pragma unroll
-        for (int e = 0; e < EPT; e += 4)
-          if (q * EPT + e < B) *reinterpret_cast<float4*>(dst + e) = make_float4(o[e], o[e + 1], o[e + 2], o[e + 3]);
-      } else {
-#pragma unroll
-        for (int e = 0; e < EPT; ++e)
-          if (q * EPT + e < B) dst[e] = o[e];
-      }
-    }
-  } else {
-    if (i < B) {
-#pragma unroll
-      for (int e = 0; e < EPT; ++e) {
-        const int j = q * EPT + e;
-        if (j < B) out[(long long)i * B + j] = g * Gr[e];
-      }
-    }
-    __syncthreads();
-    if (i < B) {
-#pragma unroll
-      for (int e = 0; e < EPT; ++e) {
-        const int r = q * EPT + e;
-        if (r < B) out[(long long)r * B + i] += g * Gc[e];
-      }
+    for (int e = 0; e < EPT; ++e) {
+      const int j = q * EPT + e;
+      if (j < B) out[(long long)i * B + j] = g * Gr[e];
     }
   }
-  SK_STAMP(1, 7);
+  __syncthreads();
+  if (i < B) {
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) {
+      const int r = q * EPT + e;
+      if (r < B) out[(long long)r * B + i] += g * Gc[e];
+    }
+  }
 }
 
 template <int EPT>
@@ -857,8 +670,7 @@ static int launch_bwd_t(const float* C, int nsolve, int B, float eps, int L, con
                                       (int)(160 * 1024)));
       attr = 160 * 1024;
     }
-    const size_t tile_bytes = (size_t)(4 * EPT) * (4 * EPT + 1) * sizeof(float);      // Cbar transposition tile of the epilogue
-    sinkhorn_bwd_small_kernel<EPT, true><<<nsolve, threads, hist_bytes > tile_bytes ? hist_bytes : tile_bytes, st>>>(C, B, eps, L, u_hist, v_hist, nits, gcost, Cbar,
+    sinkhorn_bwd_small_kernel<EPT, true><<<nsolve, threads, hist_bytes, st>>>(C, B, eps, L, u_hist, v_hist, nits, gcost, Cbar,
                                                                           only_if);
   } else {
     sinkhorn_bwd_small_kernel<EPT, false><<<nsolve, threads, 0, st>>>(C, B, eps, L, u_hist, v_hist, nits, gcost, Cbar, only_if);
@@ -876,9 +688,3 @@ int launch_sinkhorn_bwd_small(const float* C, int nsolve, int B, float eps, int 
 }
 
 }  // namespace kccot
-
-#ifdef KCCOT_SK_TRACE
-extern "C" int kccot_debug_sk_trace(long long* host_out) {
-  return (int)cudaMemcpyFromSymbol(host_out, kccot::g_sk_trace, sizeof(kccot::g_sk_trace));
-}
-#endif

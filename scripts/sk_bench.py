@@ -3,6 +3,8 @@ import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from kccotgan_b200 import functional as F, _lib
+if os.environ.get("KCCOT_LIB_PATH"):          # A/B timing against another build of the library
+    _lib.LIB_PATH = os.environ["KCCOT_LIB_PATH"]
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 5
