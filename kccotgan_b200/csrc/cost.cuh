@@ -18,6 +18,7 @@ struct CostBlock {
 };
 struct CostBlocks {
   CostBlock b[3];
+  int* zero = nullptr;     // optional [nprob] counters cleared by the finalize kernel (see SinkhornMix)
 };
 
 // One output tensor of the martingale adjoint (see martingale_bwd_kernel).
@@ -40,6 +41,10 @@ int launch_martingale_jobs(const MartJobs& jobs, int njobs, int nprob, int T, in
 void choose_ksplit_simt(int nprob, int Bx, int By, long long K, int* ksplit, long long* kslab);
 int launch_sqdist_partials_simt(const float* x, const float* y, int nprob, int Bx, int By, long long K,
                                 int ksplit, long long kslab, float* part, cudaStream_t st);
+// kccot_mixed_cost_fwd plus optional counters for the finalize kernel to clear (mixed_abi.cu)
+int mixed_cost_fwd_impl(const float* real, const float* fake, int nprob, int B, long long K, const float* h_fake,
+                        const float* m_real, const float* h_real, const float* m_fake, int T, int J, float s,
+                        float* C3, void* ws, size_t ws_bytes, int flags, void* stream, int* zero_counters);
 int launch_cost_finalize(const CostBlocks& blocks, int nblocks, int nprob, int T, int J, float s,
                          cudaStream_t st);
 int launch_cost_bwd_simt(const float* W, long long sr, long long sc, long long wprob, const float* a,

@@ -98,6 +98,15 @@ size_t kccot_mixed_cost_workspace_bytes(int nprob, int B, long long K) {
 int kccot_mixed_cost_fwd(const float* real, const float* fake, int nprob, int B, long long K, const float* h_fake,
                          const float* m_real, const float* h_real, const float* m_fake, int T, int J, float s,
                          float* C3, void* ws, size_t ws_bytes, int flags, void* stream) {
+  return kccot::mixed_cost_fwd_impl(real, fake, nprob, B, K, h_fake, m_real, h_real, m_fake, T, J, s, C3, ws, ws_bytes,
+                                    flags, stream, nullptr);
+}
+}  // extern "C"
+
+namespace kccot {
+int mixed_cost_fwd_impl(const float* real, const float* fake, int nprob, int B, long long K, const float* h_fake,
+                        const float* m_real, const float* h_real, const float* m_fake, int T, int J, float s,
+                        float* C3, void* ws, size_t ws_bytes, int flags, void* stream, int* zero_counters) {
   if (int rc = check_common(nprob, B, B, K)) return rc;
   KCCOT_CHECK_ARG(real && fake && h_fake && m_real && h_real && m_fake && C3 && ws, "null pointer");
   KCCOT_CHECK_ARG(T >= 2 && J >= 1, "martingale term needs T >= 2, J >= 1 (T=%d J=%d)", T, J);
@@ -109,6 +118,7 @@ int kccot_mixed_cost_fwd(const float* real, const float* fake, int nprob, int B,
     return KCCOT_EUNSUPPORTED;
   }
   CostBlocks blocks{};
+  blocks.zero = zero_counters;
   const long long BB = (long long)B * B;
   // order xy, xx, yy — gan_utils.py:221-223
   const float* hs[3] = {h_fake, h_real, h_fake};
@@ -147,6 +157,9 @@ int kccot_mixed_cost_fwd(const float* real, const float* fake, int nprob, int B,
   }
   return launch_cost_finalize(blocks, 3, nprob, T, J, s, st);
 }
+}  // namespace kccot
+
+extern "C" {
 
 int kccot_mixed_sqdist_partials(const float* real, const float* fake, int nprob, int B, long long K, void* ws,
                                 size_t ws_bytes, int flags, void* stream) {

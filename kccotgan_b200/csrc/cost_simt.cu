@@ -107,6 +107,7 @@ constexpr int FGmax = 8;  // k-slab groups per CTA
 
 __global__ void __launch_bounds__(128 * FGmax) cost_finalize_kernel(CostBlocks blocks, int T, int J, float s) {
   __shared__ double red[FGmax][2][FT * FT];
+  if (blocks.zero != nullptr && blockIdx.x == 0 && blockIdx.z == 0 && threadIdx.x == 0) blocks.zero[blockIdx.y] = 0;
   const CostBlock& b = blocks.b[blockIdx.z];
   const int tiles_j = (b.By + FT - 1) / FT, tiles_i = (b.Bx + FT - 1) / FT;
   if ((int)blockIdx.x >= tiles_i * tiles_j) return;
@@ -175,6 +176,7 @@ int launch_cost_finalize(const CostBlocks& blocks, int nblocks, int nprob, int T
       bl.b[i].part += (long long)p0 * bl.b[i].prob_stride;
       bl.b[i].C += (long long)p0 * bl.b[i].C_prob_stride;
       if (bl.b[i].h1) { bl.b[i].h1 += (long long)p0 * bl.b[i].Bx * T * J; bl.b[i].M1 += (long long)p0 * bl.b[i].By * T * J; }
+      if (i == 0 && bl.zero) bl.zero += p0;
       if (bl.b[i].h2) { bl.b[i].h2 += (long long)p0 * bl.b[i].Bx * T * J; bl.b[i].M2 += (long long)p0 * bl.b[i].By * T * J; }
     }
     dim3 grid((unsigned)tiles, (unsigned)np, (unsigned)nblocks);

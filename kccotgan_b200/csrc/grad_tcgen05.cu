@@ -47,6 +47,7 @@ constexpr int kObufBytes = kMaxN * 128;     // one staged output tile
 struct Bars {
   uint64_t full[kMaxStages], conv[kMaxStages], empty[kMaxStages];
   uint64_t acc_full[kAccBufs], acc_empty[kAccBufs];
+  uint64_t w_ready;                          // W' is in tensor memory (4 loader warps arrive)
   uint32_t tmem_base;
 };
 
@@ -95,7 +96,7 @@ __global__ void __launch_bounds__(128) build_w_pair_kernel(const float* __restri
 __global__ void __launch_bounds__(kThreads, 1)
 grad_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy,
                const __grid_constant__ CUtensorMap tmo, int Bx, int By, long long K, const float* __restrict__ W,
-               int row_off, int N, float neg2s, int accumulate, int nstages, long long* __restrict__ trace) {
+               const float* __restrict__ Cbar3, int row_off, int N, float neg2s, int accumulate, int nstages, long long* __restrict__ trace) {
   extern __shared__ uint8_t smem_raw[];
   // align by OFFSET so that the compiler keeps the shared address space (LDS/STS, not generic LD/ST)
   uint8_t* base = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -132,6 +133,7 @@ grad_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ 
       tc::mbar_init(&bars.acc_full[b], 1);
       tc::mbar_init(&bars.acc_empty[b], 2);                 // the two warps that own TMEM lanes 0-63
     }
+    tc::mbar_init(&bars.w_ready, kEpiWarps);
     tc::fence_barrier_init();
   }
   if (warp == 1) {
@@ -142,30 +144,98 @@ grad_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ 
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem = bars.tmem_base;
-  // W' -> tensor memory.  The four epilogue warps own one 32-lane quadrant each: thread = row, 32 contraction
-  // columns per store; tf32 hi to columns [0,128), lo to [128,256).  Rows >= N and columns >= R are zero.
+  // W' -> tensor memory, by the four epilogue warps (one 32-lane quadrant each: thread = row, 32 contraction
+  // columns per store; tf32 hi to columns [0,128), lo to [128,256); rows >= N and columns >= R are zero).
+  // The TMA producer and the converters do not wait for it: the ring fills while W' is being built; only the
+  // MMA issuer waits on w_ready.
+  //   Cbar3 == nullptr: W' was built by a separate kernel (generic pair).
+  //   Cbar3 != nullptr: mixed loss, W' is formed here from the three cost adjoints (xy, xx, yy):
+  //       x-row r:  [ Cxx[r][c] + Cxx[c][r] | Cxy[r][c'] ],   y-row j:  [ Cxy[c][j] | Cyy[j][c'] + Cyy[c'][j] ],
+  //       diagonal = -(sum of the row).  The thread holds the whole row, so the row sum needs no reduction;
+  //       the 32-column group that contains the diagonal is stored last (row_off % 32 == 0: warp-uniform).
   if (warp >= 2 + kConvWarps) {
     const int quadw = warp & 3;
     const int rr = quadw * 32 + lane;                       // A row = TMEM lane
-    const float* Wrow = W + ((long long)p * R + row_off + min(rr, N - 1)) * R;
-    for (int cg = 0; cg < 128; cg += 32) {
-      float h[32], l[32];
+    if (Cbar3 == nullptr) {
+      const float* Wrow = W + ((long long)p * R + row_off + min(rr, N - 1)) * R;
+      for (int cg = 0; cg < 128; cg += 32) {
+        float h[32], l[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int c = cg + j;
-        const float v = (rr < N && c < R) ? Wrow[c] : 0.f;
-        h[j] = tc::to_tf32(v);
-        l[j] = tc::to_tf32(v - h[j]);
+        for (int j = 0; j < 32; ++j) {
+          const int c = cg + j;
+          const float v = (rr < N && c < R) ? Wrow[c] : 0.f;
+          h[j] = tc::to_tf32(v);
+          l[j] = tc::to_tf32(v - h[j]);
+        }
+        const uint32_t ta = tmem + ((uint32_t)(quadw * 32) << 16) + (uint32_t)cg;
+        tc::tmem_st_32x32(ta, h);
+        tc::tmem_st_32x32(ta + 128, l);
       }
-      const uint32_t ta = tmem + ((uint32_t)(quadw * 32) << 16) + (uint32_t)cg;
-      tc::tmem_st_32x32(ta, h);
-      tc::tmem_st_32x32(ta + 128, l);
+    } else {
+      const int B = Bx;                                     // mixed loss: Bx == By
+      const long long BB = (long long)B * B;
+      const float* Cxy = Cbar3 + (long long)p * 3 * BB;
+      const float* Cxx = Cxy + BB;
+      const float* Cyy = Cxy + 2 * BB;
+      const int r = row_off + min(rr, N - 1);
+      const int dg = ((row_off + quadw * 32) >> 5) & 3;     // group of the diagonal (warp-uniform)
+      const bool xrow = r < B;
+      const int rl = xrow ? r : r - B;
+      float d = 0.f;
+      for (int g = 0; g < 4; ++g) {
+        const int cg = ((dg + 1 + g) & 3) * 32;
+        // B % 32 == 0: the whole warp is on x-rows or on y-rows and the whole group on one side of B, so the
+        // source block is warp-uniform and the loads are straight-line (row part: 8 x 16 bytes of this
+        // thread's row; column part: 32 loads coalesced across the warp)
+        const bool cx = cg < B;
+        const int cgl = cx ? cg : cg - B;
+        const float* blk = xrow ? (cx ? Cxx : Cxy) : (cx ? Cxy : Cyy);
+        const bool inside = cg < R;                          // groups beyond the stacked rows are zero (no loads)
+        const bool has_row = inside && (xrow || !cx), has_col = inside && (cx || !xrow);
+        float v[32];
+        if (has_row) {
+          const float4* rp = reinterpret_cast<const float4*>(blk + (long long)rl * B + cgl);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 t = rp[j];
+            v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0.f;
+        }
+        if (has_col) {
+          const float* cp = blk + (long long)cgl * B + rl;
+          float t[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) t[j] = cp[(long long)j * B];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += t[j];
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int c = cg + j;
+          v[j] = (rr < N && c < R && c != r) ? v[j] : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) d += v[j];
+        float h[32], l[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float w = (g == 3 && cg + j == r && rr < N) ? -d : v[j];
+          h[j] = tc::to_tf32(w);
+          l[j] = tc::to_tf32(w - h[j]);
+        }
+        const uint32_t ta = tmem + ((uint32_t)(quadw * 32) << 16) + (uint32_t)cg;
+        tc::tmem_st_32x32(ta, h);
+        tc::tmem_st_32x32(ta + 128, l);
+      }
     }
     tc::tmem_st_wait();
+    tc::tc_fence_before();
+    __syncwarp();
+    if (lane == 0) tc::mbar_arrive(&bars.w_ready);
   }
-  tc::tc_fence_before();
-  __syncthreads();
-  tc::tc_fence_after();
 
   if (warp == 0) {
     // ------------------------------- TMA producer ---------------------------------------------
@@ -194,6 +264,8 @@ grad_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ 
       const uint32_t lbo = (uint32_t)((size_t)nstages * stage_bytes);     // hi box -> lo box of the same stage
       int stage = 0, phase = 0;
       int ab = 0, ab_phase = 0;
+      tc::mbar_wait(&bars.w_ready, 0);
+      tc::tc_fence_after();
       for (long long t = t_begin; t < t_end; ++t) {
         tc::mbar_wait(&bars.acc_empty[ab], ab_phase ^ 1);
         tc::tc_fence_after();
@@ -364,8 +436,8 @@ bool tc_grad_supported(const float* x, const float* y, int Bx, int By, long long
 }
 
 // W: [nprob, R, R] already holds W' (diagonal = -rowsum)
-static int launch_grad_rows(const CUtensorMap& tmx, const CUtensorMap& tmy, const float* W, int nprob, int Bx, int By,
-                            long long K, float s, int row_off, int N, float* out, int accumulate, cudaStream_t st) {
+static int launch_grad_rows(const CUtensorMap& tmx, const CUtensorMap& tmy, const float* W, const float* Cbar3,
+                            int nprob, int Bx, int By, long long K, float s, int row_off, int N, float* out, int accumulate, cudaStream_t st) {
   const GradPlan g = plan_grad(Bx, By, N);
   CUtensorMap tmo;     // output [nprob][N][K], box [N x 32], 128-byte swizzle (matches the staging tile)
   if (int rc = encode_tmap_3d(&tmo, out, (uint64_t)K, (uint64_t)N, (uint64_t)nprob, (uint64_t)K * 4, (uint64_t)K * 4 * N,
@@ -381,7 +453,7 @@ static int launch_grad_rows(const CUtensorMap& tmx, const CUtensorMap& tmy, cons
   if (gx > ntiles) gx = (int)ntiles;
   if (gx < 1) gx = 1;
   dim3 grid(gx, nprob);
-  grad_tc_kernel<<<grid, kThreads, g.smem, st>>>(tmx, tmy, tmo, Bx, By, K, W, row_off, N, -2.f * s, accumulate,
+  grad_tc_kernel<<<grid, kThreads, g.smem, st>>>(tmx, tmy, tmo, Bx, By, K, W, Cbar3, row_off, N, -2.f * s, accumulate,
                                                 g.nstages, g_grad_trace);
   KCCOT_LAUNCH_CHECK();
   return KCCOT_OK;
@@ -390,8 +462,14 @@ static int launch_grad_rows(const CUtensorMap& tmx, const CUtensorMap& tmy, cons
 int launch_grad_tc(const float* Cbar3, const float* x, const float* y, int nprob, int Bx, int By, long long K, float s,
                    float* gx, float* gy, int accumulate, float* Wws, cudaStream_t st) {
   const int R = Bx + By;
-  build_w_mixed_kernel<<<dim3(R, nprob), 128, 0, st>>>(Cbar3, Bx, Wws);
-  KCCOT_LAUNCH_CHECK();
+  // Bx == By and Bx % 32 == 0: the gradient kernel forms W' itself (no separate launch); otherwise the
+  // small build kernel runs first
+  const bool fused_w = (Bx == By) && (Bx % 32 == 0) && (reinterpret_cast<uintptr_t>(Cbar3) & 15) == 0;
+  if (!fused_w) {
+    build_w_mixed_kernel<<<dim3(R, nprob), 128, 0, st>>>(Cbar3, Bx, Wws);
+    KCCOT_LAUNCH_CHECK();
+  }
+  const float* Csrc = fused_w ? Cbar3 : nullptr;
   CUtensorMap tmx, tmy;
   if (int rc = encode_tmap_3d(&tmx, x, (uint64_t)K, (uint64_t)Bx, (uint64_t)nprob, (uint64_t)K * 4, (uint64_t)K * 4 * Bx,
                               kBoxCols, (uint32_t)Bx, true))
@@ -400,9 +478,9 @@ int launch_grad_tc(const float* Cbar3, const float* x, const float* y, int nprob
                               kBoxCols, (uint32_t)By, true))
     return rc;
   if (gy)
-    if (int rc = launch_grad_rows(tmx, tmy, Wws, nprob, Bx, By, K, s, Bx, By, gy, accumulate, st)) return rc;
+    if (int rc = launch_grad_rows(tmx, tmy, Wws, Csrc, nprob, Bx, By, K, s, Bx, By, gy, accumulate, st)) return rc;
   if (gx)
-    if (int rc = launch_grad_rows(tmx, tmy, Wws, nprob, Bx, By, K, s, 0, Bx, gx, accumulate, st)) return rc;
+    if (int rc = launch_grad_rows(tmx, tmy, Wws, Csrc, nprob, Bx, By, K, s, 0, Bx, gx, accumulate, st)) return rc;
   return KCCOT_OK;
 }
 
@@ -419,9 +497,9 @@ int launch_grad_pair_tc(const float* Cbar, const float* x, const float* y, int n
                               kBoxCols, (uint32_t)By, true))
     return rc;
   if (gy)
-    if (int rc = launch_grad_rows(tmx, tmy, Wws, nprob, Bx, By, K, s, Bx, By, gy, accumulate, st)) return rc;
+    if (int rc = launch_grad_rows(tmx, tmy, Wws, nullptr, nprob, Bx, By, K, s, Bx, By, gy, accumulate, st)) return rc;
   if (gx)
-    if (int rc = launch_grad_rows(tmx, tmy, Wws, nprob, Bx, By, K, s, 0, Bx, gx, accumulate, st)) return rc;
+    if (int rc = launch_grad_rows(tmx, tmy, Wws, nullptr, nprob, Bx, By, K, s, 0, Bx, gx, accumulate, st)) return rc;
   return KCCOT_OK;
 }
 

@@ -6,7 +6,7 @@
 namespace kccot {
 namespace {
 struct SavedLayout {
-  size_t off_C3, off_uh, off_vh, off_nits, off_cost, total;
+  size_t off_C3, off_uh, off_vh, off_nits, off_cost, off_cnt, total;
 };
 SavedLayout saved_layout(int nprob, int B, int L) {
   SavedLayout s;
@@ -16,6 +16,7 @@ SavedLayout saved_layout(int nprob, int B, int L) {
   s.off_vh = o; o += align_up((size_t)nprob * 3 * (L + 1) * B * 4, 256);
   s.off_nits = o; o += align_up((size_t)nprob * 3 * 4, 256);
   s.off_cost = o; o += align_up((size_t)nprob * 3 * 4, 256);
+  s.off_cnt = o; o += align_up((size_t)nprob * 4, 256);     // triple-completion counters (SinkhornMix)
   s.total = o;
   return s;
 }
@@ -67,10 +68,20 @@ int kccot_mixed_loss_fwd(const float* real, const float* fake, int nprob, int B,
   const SavedLayout sl = saved_layout(nprob, B, L);
   char* sv = (char*)saved;
   float* C3 = (float*)(sv + sl.off_C3);
-  if (int rc = kccot_mixed_cost_fwd(real, fake, nprob, B, K, h_fake, m_real, h_real, m_fake, T, J, s, C3, ws, ws_bytes,
-                                    flags, stream))
+  const bool small = B <= kSmallSinkhornMaxB;      // loss combination folded into the Sinkhorn kernel
+  int* counters = (int*)(sv + sl.off_cnt);
+  if (int rc = mixed_cost_fwd_impl(real, fake, nprob, B, K, h_fake, m_real, h_real, m_fake, T, J, s, C3, ws, ws_bytes,
+                                   flags, stream, small ? counters : nullptr))
     return rc;
   // Lmin = 100, thresh = 1e-2, break on the iteration COUNT: compute_sinkhorn, gan_utils.py:144-160
+  if (small) {
+    SinkhornMix mix;
+    mix.loss = loss; mix.terms = terms; mix.counter = counters;
+    KCCOT_CHECK_ARG(L >= 0 && eps > 0.f, "bad eps / L");
+    return launch_sinkhorn_fwd_small(C3, 3 * nprob, B, eps, L, 100, 1e-2f, 0, (float*)(sv + sl.off_uh),
+                                     (float*)(sv + sl.off_vh), (int32_t*)(sv + sl.off_nits), (float*)(sv + sl.off_cost),
+                                     (cudaStream_t)stream, mix);
+  }
   if (int rc = kccot_sinkhorn_fwd(C3, 3 * nprob, B, eps, L, 100, 1e-2f, 0, (float*)(sv + sl.off_uh),
                                   (float*)(sv + sl.off_vh), (int32_t*)(sv + sl.off_nits), (float*)(sv + sl.off_cost), ws,
                                   ws_bytes, stream))
@@ -96,12 +107,22 @@ int kccot_mixed_loss_bwd(const float* gloss, const float* real, const float* fak
   float* gcost = (float*)((char*)ws + cb_bytes);
   void* ws2 = (char*)ws + cb_bytes + gc_bytes;
   const size_t ws2_bytes = ws_bytes - cb_bytes - gc_bytes;
-  expand_gloss_kernel<<<(nprob + 127) / 128, 128, 0, (cudaStream_t)stream>>>(gloss, nprob, gcost);
-  KCCOT_LAUNCH_CHECK();
-  if (int rc = kccot_sinkhorn_bwd((const float*)(sv + sl.off_C3), 3 * nprob, B, eps, L, (const float*)(sv + sl.off_uh),
-                                  (const float*)(sv + sl.off_vh), (const int32_t*)(sv + sl.off_nits), gcost, Cbar3, ws2,
-                                  ws2_bytes, stream))
-    return rc;
+  if (B <= kSmallSinkhornMaxB) {                   // the 2, -1, -1 weights are applied inside the kernel
+    SinkhornMix mix;
+    mix.gloss = gloss;
+    if (int rc = launch_sinkhorn_bwd_small((const float*)(sv + sl.off_C3), 3 * nprob, B, eps, L,
+                                           (const float*)(sv + sl.off_uh), (const float*)(sv + sl.off_vh),
+                                           (const int32_t*)(sv + sl.off_nits), nullptr, Cbar3, nullptr,
+                                           (cudaStream_t)stream, mix))
+      return rc;
+  } else {
+    expand_gloss_kernel<<<(nprob + 127) / 128, 128, 0, (cudaStream_t)stream>>>(gloss, nprob, gcost);
+    KCCOT_LAUNCH_CHECK();
+    if (int rc = kccot_sinkhorn_bwd((const float*)(sv + sl.off_C3), 3 * nprob, B, eps, L, (const float*)(sv + sl.off_uh),
+                                    (const float*)(sv + sl.off_vh), (const int32_t*)(sv + sl.off_nits), gcost, Cbar3, ws2,
+                                    ws2_bytes, stream))
+      return rc;
+  }
   return kccot_mixed_cost_bwd(Cbar3, real, fake, nprob, B, K, h_fake, m_real, h_real, m_fake, T, J, s, g_real, g_fake,
                               gh_fake, gm_real, gh_real, gm_fake, ws2, ws2_bytes, flags, stream);
 }

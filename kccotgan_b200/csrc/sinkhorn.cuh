@@ -7,13 +7,24 @@ namespace kccot {
 constexpr int kSmallSinkhornMaxB = 64;   // register-resident single-CTA path
 constexpr int kRowChunk = 32;            // rows per CTA in the streamed path
 
+// Epilogue / prologue of the mixed loss folded into the small kernels (problems come in triples xy, xx, yy):
+//   forward : the CTA of a triple that finishes last writes loss[p] = 2 xy - xx - yy (gan_utils.py:225) and the
+//             three terms; `counter[p]` must be zero when the kernel starts (cost_finalize_kernel clears it)
+//   backward: the upstream gradient of problem n is gloss[n / 3] * (n % 3 == 0 ? 2 : -1)
+struct SinkhornMix {
+  float* loss = nullptr;
+  float* terms = nullptr;
+  int* counter = nullptr;
+  const float* gloss = nullptr;
+};
+
 // sinkhorn_small.cu
 int launch_sinkhorn_fwd_small(const float* C, int nsolve, int B, float eps, int L, int Lmin, float thresh,
                               int exit_on_index, float* u_hist, float* v_hist, int32_t* nits, float* cost,
-                              cudaStream_t st);
+                              cudaStream_t st, SinkhornMix mix = SinkhornMix());
 int launch_sinkhorn_bwd_small(const float* C, int nsolve, int B, float eps, int L, const float* u_hist,
                               const float* v_hist, const int32_t* nits, const float* gcost, float* Cbar,
-                              const int32_t* only_if, cudaStream_t st);
+                              const int32_t* only_if, cudaStream_t st, SinkhornMix mix = SinkhornMix());
 
 
 // sinkhorn_stream.cu — any B; C streamed from L2/HBM; a kernel boundary per half-iteration pair.

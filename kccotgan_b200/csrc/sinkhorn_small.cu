@@ -187,7 +187,7 @@ template <int EPT, bool HS>
 __global__ void __launch_bounds__(4 * 4 * EPT) sinkhorn_fwd_small_kernel(
     const float* __restrict__ C, int B, float eps, int L, int Lmin, float thresh, int exit_on_index,
     float* __restrict__ u_hist, float* __restrict__ v_hist, int32_t* __restrict__ nits_out,
-    float* __restrict__ cost_out) {
+    float* __restrict__ cost_out, SinkhornMix mix) {
   constexpr int BM = 4 * EPT;
   constexpr int BMP = 4 * (EPT + 4);
   extern __shared__ __align__(16) float hist[];         // HS: Uh[L+1][BM] | Vh[L+1][BM]
@@ -424,6 +424,17 @@ __global__ void __launch_bounds__(4 * 4 * EPT) sinkhorn_fwd_small_kernel(
   if (tid == 0) {
     cost_out[n] = s1 / kscale + c0 * s0;
     nits_out[n] = nits;
+    if (mix.loss != nullptr) {                          // last CTA of the triple combines the three terms
+      __threadfence();
+      const int p = n / 3;
+      if (atomicAdd(&mix.counter[p], 1) == 2) {
+        __threadfence();
+        const volatile float* cv = cost_out + 3 * p;
+        const float xy = cv[0], xx = cv[1], yy = cv[2];
+        mix.loss[p] = 2.f * xy - xx - yy;               // gan_utils.py:225
+        if (mix.terms) { mix.terms[3 * p] = xy; mix.terms[3 * p + 1] = xx; mix.terms[3 * p + 2] = yy; }
+      }
+    }
   }
   SK_STAMP(0, 4);
   if (HS) {
@@ -458,7 +469,7 @@ template <int EPT, bool HS>
 __global__ void __launch_bounds__(4 * 4 * EPT) sinkhorn_bwd_small_kernel(
     const float* __restrict__ C, int B, float eps, int L, const float* __restrict__ u_hist,
     const float* __restrict__ v_hist, const int32_t* __restrict__ nits_in, const float* __restrict__ gcost,
-    float* __restrict__ Cbar, const int32_t* __restrict__ only_if) {
+    float* __restrict__ Cbar, const int32_t* __restrict__ only_if, SinkhornMix mix) {
   if (only_if != nullptr && only_if[blockIdx.x] == 0) return;     // fallback launch: only the declined problems
   constexpr int BM = 4 * EPT;
   constexpr int PQ = EPT + 4;                           // padded chunk stride (see pad_index)
@@ -485,7 +496,7 @@ __global__ void __launch_bounds__(4 * 4 * EPT) sinkhorn_bwd_small_kernel(
   const float* uh = u_hist + (long long)n * (L + 1) * B;
   const float* vh = v_hist + (long long)n * (L + 1) * B;
   const int nits = nits_in[n];
-  const float g = gcost[n];
+  const float g = mix.gloss ? mix.gloss[n / 3] * ((n % 3 == 0) ? 2.f : -1.f) : gcost[n];
   float* Uh = hist;
   float* Vh = hist + (HS ? (size_t)(nits + 1) * BMP : 0);
 
@@ -817,7 +828,7 @@ __global__ void __launch_bounds__(4 * 4 * EPT) sinkhorn_bwd_small_kernel(
 
 template <int EPT>
 static int launch_fwd_t(const float* C, int nsolve, int B, float eps, int L, int Lmin, float thresh, int exit_on_index,
-                        float* u_hist, float* v_hist, int32_t* nits, float* cost, int threads, cudaStream_t st) {
+                        float* u_hist, float* v_hist, int32_t* nits, float* cost, int threads, cudaStream_t st, SinkhornMix mix) {
   const size_t hist_bytes = (size_t)2 * (L + 1) * 4 * EPT * sizeof(float);
   if (hist_bytes <= 160 * 1024) {
     static bool attr = false;
@@ -827,10 +838,10 @@ static int launch_fwd_t(const float* C, int nsolve, int B, float eps, int L, int
       attr = true;
     }
     sinkhorn_fwd_small_kernel<EPT, true><<<nsolve, threads, hist_bytes, st>>>(C, B, eps, L, Lmin, thresh, exit_on_index,
-                                                                          u_hist, v_hist, nits, cost);
+                                                                          u_hist, v_hist, nits, cost, mix);
   } else {
     sinkhorn_fwd_small_kernel<EPT, false><<<nsolve, threads, 0, st>>>(C, B, eps, L, Lmin, thresh, exit_on_index, u_hist,
-                                                                    v_hist, nits, cost);
+                                                                    v_hist, nits, cost, mix);
   }
   KCCOT_LAUNCH_CHECK();
   return KCCOT_OK;
@@ -838,17 +849,17 @@ static int launch_fwd_t(const float* C, int nsolve, int B, float eps, int L, int
 
 int launch_sinkhorn_fwd_small(const float* C, int nsolve, int B, float eps, int L, int Lmin, float thresh,
                               int exit_on_index, float* u_hist, float* v_hist, int32_t* nits, float* cost,
-                              cudaStream_t st) {
+                              cudaStream_t st, SinkhornMix mix) {
   const int threads = ((4 * B + 31) / 32) * 32;
   if (B <= 32)
-    return launch_fwd_t<8>(C, nsolve, B, eps, L, Lmin, thresh, exit_on_index, u_hist, v_hist, nits, cost, threads, st);
-  return launch_fwd_t<16>(C, nsolve, B, eps, L, Lmin, thresh, exit_on_index, u_hist, v_hist, nits, cost, threads, st);
+    return launch_fwd_t<8>(C, nsolve, B, eps, L, Lmin, thresh, exit_on_index, u_hist, v_hist, nits, cost, threads, st, mix);
+  return launch_fwd_t<16>(C, nsolve, B, eps, L, Lmin, thresh, exit_on_index, u_hist, v_hist, nits, cost, threads, st, mix);
 }
 
 template <int EPT>
 static int launch_bwd_t(const float* C, int nsolve, int B, float eps, int L, const float* u_hist, const float* v_hist,
                         const int32_t* nits, const float* gcost, float* Cbar, const int32_t* only_if, int threads,
-                        cudaStream_t st) {
+                        cudaStream_t st, SinkhornMix mix) {
   const size_t hist_bytes = (size_t)2 * (L + 1) * 4 * (EPT + 4) * sizeof(float);
   if (hist_bytes <= 160 * 1024) {
     static size_t attr = 0;
@@ -859,9 +870,9 @@ static int launch_bwd_t(const float* C, int nsolve, int B, float eps, int L, con
     }
     const size_t tile_bytes = (size_t)(4 * EPT) * (4 * EPT + 1) * sizeof(float);      // Cbar transposition tile of the epilogue
     sinkhorn_bwd_small_kernel<EPT, true><<<nsolve, threads, hist_bytes > tile_bytes ? hist_bytes : tile_bytes, st>>>(C, B, eps, L, u_hist, v_hist, nits, gcost, Cbar,
-                                                                          only_if);
+                                                                          only_if, mix);
   } else {
-    sinkhorn_bwd_small_kernel<EPT, false><<<nsolve, threads, 0, st>>>(C, B, eps, L, u_hist, v_hist, nits, gcost, Cbar, only_if);
+    sinkhorn_bwd_small_kernel<EPT, false><<<nsolve, threads, 0, st>>>(C, B, eps, L, u_hist, v_hist, nits, gcost, Cbar, only_if, mix);
   }
   KCCOT_LAUNCH_CHECK();
   return KCCOT_OK;
@@ -869,10 +880,10 @@ static int launch_bwd_t(const float* C, int nsolve, int B, float eps, int L, con
 
 int launch_sinkhorn_bwd_small(const float* C, int nsolve, int B, float eps, int L, const float* u_hist,
                               const float* v_hist, const int32_t* nits, const float* gcost, float* Cbar,
-                              const int32_t* only_if, cudaStream_t st) {
+                              const int32_t* only_if, cudaStream_t st, SinkhornMix mix) {
   const int threads = ((4 * B + 31) / 32) * 32;
-  if (B <= 32) return launch_bwd_t<8>(C, nsolve, B, eps, L, u_hist, v_hist, nits, gcost, Cbar, only_if, threads, st);
-  return launch_bwd_t<16>(C, nsolve, B, eps, L, u_hist, v_hist, nits, gcost, Cbar, only_if, threads, st);
+  if (B <= 32) return launch_bwd_t<8>(C, nsolve, B, eps, L, u_hist, v_hist, nits, gcost, Cbar, only_if, threads, st, mix);
+  return launch_bwd_t<16>(C, nsolve, B, eps, L, u_hist, v_hist, nits, gcost, Cbar, only_if, threads, st, mix);
 }
 
 }  // namespace kccot
