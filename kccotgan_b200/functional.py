@@ -218,6 +218,7 @@ class MixedLossFn(torch.autograd.Function):
         ctx.meta = (real.shape, fake.shape, float(s), float(eps), L)
         loss, terms = out[0], out[1:]
         ctx.mark_non_differentiable(terms)
+        ctx.set_materialize_grads(False)          # no zero-fill kernel for the unused gradient of `terms`
         return loss, terms
 
     @staticmethod
@@ -228,6 +229,8 @@ class MixedLossFn(torch.autograd.Function):
         T, J = h_fake.shape[1], h_fake.shape[2]
         dev = R.device
         need = ctx.needs_input_grad
+        if gloss is None:                         # loss itself unused downstream
+            return (None,) * 9
         gloss = gloss.reshape(1)
         if gloss.dtype != torch.float32 or not gloss.is_contiguous():
             gloss = gloss.float().contiguous()

@@ -33,6 +33,7 @@ class GraphedSinkhornLoss:
         self._leaves = [b for b in bufs if b.requires_grad]
         self._leaf_names = [n for b, n in zip(bufs, _NAMES) if b.requires_grad]
         dev = bufs[0].device
+        self._one = torch.ones((), dtype=torch.float32, device=dev)   # static gradient seed (no fill kernel per step)
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):                     # warm-up outside capture (attribute setting, caches)
@@ -50,7 +51,7 @@ class GraphedSinkhornLoss:
     def _eager(self):
         loss = gan_utils.compute_sinkhorn_loss(self.real, self.fake, self.scaling_coef, 0.8, 100, self.h_fake,
                                                self.m_real, self.h_real, self.m_fake, video=self.real.dim() == 5)
-        return loss, torch.autograd.grad(loss, self._leaves)
+        return loss, torch.autograd.grad(loss, self._leaves, grad_outputs=self._one)
 
     def step(self):
         """Replay: recomputes .loss and .grads from the current contents of the static inputs."""
