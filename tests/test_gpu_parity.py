@@ -198,6 +198,56 @@ def test_mixed_loss_full_size(gu, name, kind, path):
 
 
 # ---------------------------------------------------------------------------------------------
+# independent problems in one call (BASELINE config 4's shape of work) and shapes off the fast path,
+# through the raw C ABI, every problem against the fp64 oracle
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("nprob,B,T,D,path", [
+    (5, 16, 5, 96, "tcgen05"),      # batched, W' built by the separate kernel (B % 32 != 0)
+    (3, 32, 4, 64, "tcgen05"),      # batched, W' formed inside the gradient kernel
+    (4, 64, 3, 40, "auto"),         # batched at the bench's B
+    (2, 24, 6, 50, "auto"),         # K % 4 != 0 ... (T*D = 300 is a multiple of 4; B = 24 is off the 32-row W' path)
+    (3, 20, 5, 33, "simt"),         # K = 165: CUDA-core kernels only
+    (1, 9, 4, 7, "auto"),           # tiny, ragged everything
+])
+def test_mixed_loss_batched_abi(nprob, B, T, D, path):
+    import ctypes
+    from kccotgan_b200 import _lib, functional as F
+    from oracle import closed_form as cf
+    lib = _lib.load()
+    J, s, L = 6, 1.0 / 7.0, 100
+    K = T * D
+    g = torch.Generator().manual_seed(100 * nprob + B)
+    real = torch.rand((nprob, B, T, D), generator=g)
+    fake = (real + 0.3 * torch.rand((nprob, B, T, D), generator=g)).clamp_(0, 1)
+    hm = [torch.sigmoid(torch.randn((nprob, B, T, J), generator=g)) for _ in range(4)]     # h_fake, m_real, h_real, m_fake
+    d = [t.cuda().contiguous() for t in (real, fake, *hm)]
+    saved = torch.empty(lib.kccot_mixed_loss_saved_bytes(nprob, B, L), dtype=torch.uint8, device="cuda")
+    ws = torch.empty(lib.kccot_mixed_loss_workspace_bytes(nprob, B, K, L), dtype=torch.uint8, device="cuda")
+    loss = torch.full((nprob,), float("nan"), device="cuda")
+    terms = torch.full((nprob, 3), float("nan"), device="cuda")
+    flags = {"auto": 0, "simt": 1, "tcgen05": 2}[path]
+    st = F._stream(d[0].device)
+    p = F._ptr
+    _lib.call("kccot_mixed_loss_fwd", p(d[0]), p(d[1]), nprob, B, K, p(d[2]), p(d[3]), p(d[4]), p(d[5]), T, J, s, 1.0, L,
+              p(saved), p(loss), p(terms), p(ws), ws.numel(), flags, st)
+    gl = torch.linspace(0.5, 1.5, nprob, device="cuda")                 # a different upstream gradient per problem
+    grads = [torch.full_like(t, float("nan")) for t in d]
+    _lib.call("kccot_mixed_loss_bwd", p(gl), p(d[0]), p(d[1]), nprob, B, K, p(d[2]), p(d[3]), p(d[4]), p(d[5]), T, J, s,
+              1.0, L, p(saved), *[p(t) for t in grads], p(ws), ws.numel(), flags, st)
+    torch.cuda.synchronize()
+    for q in range(nprob):
+        a = [t[q].numpy().astype(np.float64) for t in (real, fake, *hm)]
+        ref, gref, det = cf.compute_sinkhorn_loss(a[0], a[1], s, 0.8, 100, a[2], a[3], a[4], a[5], grad=True)
+        ref_terms = np.array([det["loss_xy"], det["loss_xx"], det["loss_yy"]])
+        scale = np.abs(ref_terms).max()
+        assert np.abs(terms[q].cpu().numpy() - ref_terms).max() <= LOSS_TOL * scale, (q, terms[q], ref_terms)
+        assert abs(float(loss[q]) - ref) <= LOSS_TOL * scale
+        for n, t in zip(GRAD_NAMES, grads):
+            e = rel_l2(t[q].cpu().numpy().astype(np.float64) / float(gl[q]), gref[n])
+            assert e < GRAD_TOL, (q, n, e)
+
+
+# ---------------------------------------------------------------------------------------------
 # Sinkhorn kernels in isolation against the fp64 oracle on the same (fp32-rounded) cost
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("B,eps,L", [(64, 1.0, 100), (32, 0.8, 100), (17, 0.3, 40), (64, 1.0, 250), (96, 1.0, 60),
