@@ -373,6 +373,28 @@ def test_smoothing_full_frame():
         assert rel_l2(gx.cpu().numpy(), rg) < GRAD_TOL, mode
 
 
+@pytest.mark.parametrize("shape", [(2, 9, 7, 10, 1), (3, 16, 5, 12, 3), (1, 4, 4, 5, 2), (2, 64, 20, 64, 1),
+                                   (2, 12, 9, 7, 4), (5, 8, 64, 6, 1)])
+def test_smoothing_shapes(shape):
+    """Shapes that exercise both filter kernels (register-window columns, shared-memory tiles), the scalar
+    (inner % 4 != 0) and vector paths, single-channel frames and the axis-length limits."""
+    from kccotgan_b200.data_utils import KernelSmoothing
+    from oracle import closed_form as cf
+    ks = KernelSmoothing(6, 6)
+    g = torch.Generator().manual_seed(sum(shape))
+    x = torch.rand(shape, generator=g)
+    go = torch.randn(shape, generator=g)
+    for mode, fn, cfn in (("1d", ks.temporal_convolution, cf.temporal_convolution),
+                          ("3d", ks.gaussian_convolution3D, cf.gaussian_convolution3D)):
+        xl = x.cuda().requires_grad_(True)
+        out = fn(xl, 2.5)
+        gx, = torch.autograd.grad(out, xl, go.cuda())
+        ro, rg = cfn(x.numpy(), 2.5, grad_out=go.numpy())
+        assert float(out.max()) == 1.0
+        assert rel_l2(out.detach().cpu().numpy(), ro) < 1e-5, (mode, shape)
+        assert rel_l2(gx.cpu().numpy(), rg) < GRAD_TOL, (mode, shape)
+
+
 def test_errors_raise(gu):
     x = torch.rand(8, 4, 16, device="cuda")
     with pytest.raises(ValueError):
