@@ -43,6 +43,30 @@ inline void count_launch(int n = 1) { g_launches.fetch_add((unsigned long long)n
   } while (0)
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Programmatic dependent launch (sm_90+).  A kernel launched with launch_pdl() may start while the previous
+// kernel of the stream is still running, once every CTA of that kernel has executed pdl_launch_dependents()
+// (or exited); it must execute pdl_wait() before touching anything the previous kernel writes.  Rule used
+// throughout: a kernel calls pdl_launch_dependents() only AFTER its own pdl_wait(), so whatever a dependent
+// reads before its wait was complete when its predecessor's wait returned (dependencies stay transitive).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 int num_sms();
 
 struct SideLane {

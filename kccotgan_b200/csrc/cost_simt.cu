@@ -107,6 +107,8 @@ constexpr int FGmax = 8;  // k-slab groups per CTA
 
 __global__ void __launch_bounds__(128 * FGmax) cost_finalize_kernel(CostBlocks blocks, int T, int J, float s) {
   __shared__ double red[FGmax][2][FT * FT];
+  pdl_wait();                    // the partial tiles come from the kernel before
+  pdl_launch_dependents();
   if (blocks.zero != nullptr && blockIdx.x == 0 && blockIdx.z == 0 && threadIdx.x == 0) blocks.zero[blockIdx.y] = 0;
   const CostBlock& b = blocks.b[blockIdx.z];
   const int tiles_j = (b.By + FT - 1) / FT, tiles_i = (b.Bx + FT - 1) / FT;
@@ -180,7 +182,7 @@ int launch_cost_finalize(const CostBlocks& blocks, int nblocks, int nprob, int T
       if (bl.b[i].h2) { bl.b[i].h2 += (long long)p0 * bl.b[i].Bx * T * J; bl.b[i].M2 += (long long)p0 * bl.b[i].By * T * J; }
     }
     dim3 grid((unsigned)tiles, (unsigned)np, (unsigned)nblocks);
-    cost_finalize_kernel<<<grid, 128 * G, 0, st>>>(bl, T, J, s);
+    KCCOT_CUDA(launch_pdl(cost_finalize_kernel, grid, dim3(128 * G), (size_t)0, st, bl, T, J, s));
     KCCOT_LAUNCH_CHECK();
   }
   return KCCOT_OK;

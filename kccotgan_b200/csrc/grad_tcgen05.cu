@@ -37,7 +37,7 @@ constexpr int kConvWarps = 8;
 constexpr int kConvThreads = kConvWarps * 32;
 constexpr int kEpiWarps = 4;
 constexpr int kThreads = 64 + kConvThreads + kEpiWarps * 32;   // 320
-constexpr int kMaxStages = 12;
+constexpr int kMaxStages = 9;               // 162 KB: leaves room for a martingale CTA (44 KB) on the same SM; 12 measured no faster
 constexpr int kAccBufs = 4;
 constexpr int kAccCols = 64;               // per tile: [W.Zhi | W.Zlo], 32 columns each
 constexpr int kTmemCols = 512;             // W'hi [0,128) | W'lo [128,256) | 4 accumulator buffers x 64 columns
@@ -154,6 +154,7 @@ grad_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ 
   //       diagonal = -(sum of the row).  The thread holds the whole row, so the row sum needs no reduction;
   //       the 32-column group that contains the diagonal is stored last (row_off % 32 == 0: warp-uniform).
   if (warp >= 2 + kConvWarps) {
+    pdl_wait();      // Cbar3 / W come from the kernel before; the TMA producer and the converters (videos only) run ahead
     const int quadw = warp & 3;
     const int rr = quadw * 32 + lane;                       // A row = TMEM lane
     if (Cbar3 == nullptr) {
@@ -453,8 +454,8 @@ static int launch_grad_rows(const CUtensorMap& tmx, const CUtensorMap& tmy, cons
   if (gx > ntiles) gx = (int)ntiles;
   if (gx < 1) gx = 1;
   dim3 grid(gx, nprob);
-  grad_tc_kernel<<<grid, kThreads, g.smem, st>>>(tmx, tmy, tmo, Bx, By, K, W, Cbar3, row_off, N, -2.f * s, accumulate,
-                                                g.nstages, g_grad_trace);
+  KCCOT_CUDA(launch_pdl(grad_tc_kernel, grid, dim3(kThreads), g.smem, st, tmx, tmy, tmo, Bx, By, K, W, Cbar3, row_off, N,
+                        -2.f * s, accumulate, g.nstages, g_grad_trace));
   KCCOT_LAUNCH_CHECK();
   return KCCOT_OK;
 }

@@ -84,6 +84,7 @@ sqdist_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem = S.tmem_base;
+  pdl_launch_dependents();       // launched with a full dependency: lets cost_finalize_kernel's CTAs take their seats
 
   if (warp == 0) {
     // ------------------------------- TMA producer ---------------------------------------------

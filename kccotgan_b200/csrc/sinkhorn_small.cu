@@ -204,6 +204,8 @@ __global__ void __launch_bounds__(4 * 4 * EPT) sinkhorn_fwd_small_kernel(
   const float two_ahat = 1.f / (float)B;
   float Cr[EPT], Cc[EPT], Kr[EPT], Kc[EPT];
   SK_STAMP(0, 0);
+  pdl_wait();                    // C comes from the kernel before (cost_finalize_kernel in the fused path)
+  pdl_launch_dependents();       // the backward kernel may load its cost slices while this one iterates
   const float c0 = load_slices<EPT>(C + (long long)n * B * B, B, kscale, red, Cr, Cc);
   SK_STAMP(0, 1);
   float* uh = u_hist + (long long)n * (L + 1) * B;
@@ -491,7 +493,9 @@ __global__ void __launch_bounds__(4 * 4 * EPT) sinkhorn_bwd_small_kernel(
   const float ahat = -log2f((float)B);
   float Cr[EPT], Cc[EPT], Kr[EPT], Kc[EPT], Gr[EPT], Gc[EPT];
   SK_STAMP(1, 0);
-  load_slices<EPT>(C + (long long)n * B * B, B, kscale, red, Cr, Cc);
+  load_slices<EPT>(C + (long long)n * B * B, B, kscale, red, Cr, Cc);   // C predates the forward kernel: safe before the wait
+  pdl_wait();                    // history, nits, upstream gradient come from the kernels before
+  pdl_launch_dependents();       // the gradient GEMM may start streaming the videos now
   SK_STAMP(1, 1);
   const float* uh = u_hist + (long long)n * (L + 1) * B;
   const float* vh = v_hist + (long long)n * (L + 1) * B;
@@ -837,11 +841,11 @@ static int launch_fwd_t(const float* C, int nsolve, int B, float eps, int L, int
                                       (int)(160 * 1024)));
       attr = true;
     }
-    sinkhorn_fwd_small_kernel<EPT, true><<<nsolve, threads, hist_bytes, st>>>(C, B, eps, L, Lmin, thresh, exit_on_index,
-                                                                          u_hist, v_hist, nits, cost, mix);
+    KCCOT_CUDA(launch_pdl(sinkhorn_fwd_small_kernel<EPT, true>, dim3(nsolve), dim3(threads), hist_bytes, st, C, B, eps, L, Lmin,
+                          thresh, exit_on_index, u_hist, v_hist, nits, cost, mix));
   } else {
-    sinkhorn_fwd_small_kernel<EPT, false><<<nsolve, threads, 0, st>>>(C, B, eps, L, Lmin, thresh, exit_on_index, u_hist,
-                                                                    v_hist, nits, cost, mix);
+    KCCOT_CUDA(launch_pdl(sinkhorn_fwd_small_kernel<EPT, false>, dim3(nsolve), dim3(threads), (size_t)0, st, C, B, eps, L, Lmin,
+                          thresh, exit_on_index, u_hist, v_hist, nits, cost, mix));
   }
   KCCOT_LAUNCH_CHECK();
   return KCCOT_OK;
@@ -869,10 +873,12 @@ static int launch_bwd_t(const float* C, int nsolve, int B, float eps, int L, con
       attr = 160 * 1024;
     }
     const size_t tile_bytes = (size_t)(4 * EPT) * (4 * EPT + 1) * sizeof(float);      // Cbar transposition tile of the epilogue
-    sinkhorn_bwd_small_kernel<EPT, true><<<nsolve, threads, hist_bytes > tile_bytes ? hist_bytes : tile_bytes, st>>>(C, B, eps, L, u_hist, v_hist, nits, gcost, Cbar,
-                                                                          only_if, mix);
+    KCCOT_CUDA(launch_pdl(sinkhorn_bwd_small_kernel<EPT, true>, dim3(nsolve), dim3(threads),
+                          hist_bytes > tile_bytes ? hist_bytes : tile_bytes, st, C, B, eps, L, u_hist, v_hist, nits, gcost,
+                          Cbar, only_if, mix));
   } else {
-    sinkhorn_bwd_small_kernel<EPT, false><<<nsolve, threads, 0, st>>>(C, B, eps, L, u_hist, v_hist, nits, gcost, Cbar, only_if, mix);
+    KCCOT_CUDA(launch_pdl(sinkhorn_bwd_small_kernel<EPT, false>, dim3(nsolve), dim3(threads), (size_t)0, st, C, B, eps, L,
+                          u_hist, v_hist, nits, gcost, Cbar, only_if, mix));
   }
   KCCOT_LAUNCH_CHECK();
   return KCCOT_OK;
