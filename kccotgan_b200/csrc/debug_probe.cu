@@ -54,6 +54,90 @@ tma_stream_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant_
   }
   if (acc == 123.456f) *sink = acc;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Mat-vec iteration probe: the scaling-form Sinkhorn loop at B = 64 with LPR lanes per row
+// (LPR = 4 is the product kernel's mapping; 2 and 1 trade shuffles and barrier width against longer
+// FMA chains).  Reports clock64 cycles per iteration of CTA 0.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t probe_pin(uint32_t v) {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v));
+  return r;
+}
+__device__ __forceinline__ float4 probe_lds128(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void probe_sts(uint32_t a, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory");
+}
+
+template <int LPR>
+__global__ void __launch_bounds__(64 * LPR) matvec_probe_kernel(const float* __restrict__ C, int iters,
+                                                                long long* cycles, float* ab_out) {
+  constexpr int B = 64, EPT = B / LPR, PQ = EPT + 4;
+  __shared__ __align__(16) float as[LPR * PQ], bs[LPR * PQ];
+  __shared__ float hist[2][32][B];
+  const int tid = threadIdx.x, i = tid / LPR, q = tid % LPR;
+  float Kr[EPT], Kc[EPT];
+#pragma unroll
+  for (int e = 0; e < EPT; ++e) {
+    Kr[e] = exp2f(-0.05f * fabsf(C[i * B + q * EPT + e] - 900.f));
+    Kc[e] = exp2f(-0.05f * fabsf(C[(q * EPT + e) * B + i] - 900.f));
+  }
+  const int ip = (i / EPT) * PQ + (i % EPT);
+  for (int t = tid; t < LPR * PQ; t += blockDim.x) { as[t] = 0.f; bs[t] = 0.f; }
+  __syncthreads();
+  if (q == 0) bs[ip] = 1.f;
+  __syncthreads();
+  const uint32_t as_q = probe_pin((uint32_t)__cvta_generic_to_shared(as) + q * PQ * 4);
+  const uint32_t bs_q = probe_pin((uint32_t)__cvta_generic_to_shared(bs) + q * PQ * 4);
+  const uint32_t as_i = probe_pin((uint32_t)__cvta_generic_to_shared(&as[ip]));
+  const uint32_t bs_i = probe_pin((uint32_t)__cvta_generic_to_shared(&bs[ip]));
+  const uint32_t h_i = probe_pin((uint32_t)__cvta_generic_to_shared(&hist[0][0][i]));
+  const float c = 1.f / 64.f;
+  auto dot = [&](const float (&Ks)[EPT], uint32_t a) {
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+    for (int e = 0; e < EPT; e += 4) {
+      const float4 b = probe_lds128(a + e * 4);
+      s0 = fmaf(Ks[e], b.x, s0); s1 = fmaf(Ks[e + 1], b.y, s1); s2 = fmaf(Ks[e + 2], b.z, s2); s3 = fmaf(Ks[e + 3], b.w, s3);
+    }
+    float s = (s0 + s1) + (s2 + s3);
+#pragma unroll
+    for (int o = 1; o < LPR; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    return s;
+  };
+  const long long t0 = clock64();
+  float a_new = 0.f, b_new = 0.f;
+  for (int it = 0; it < iters; ++it) {
+    const float s = dot(Kr, bs_q);
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(s));
+    a_new = c * r;
+    float lg;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(s));
+    if (q == 0) {
+      probe_sts(as_i, a_new);
+      probe_sts(h_i + (uint32_t)(it & 31) * (B * 4), -lg);
+    }
+    __syncthreads();
+    const float t = dot(Kc, as_q);
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t));
+    b_new = c * r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(t));
+    if (q == 0) {
+      probe_sts(bs_i, b_new);
+      probe_sts(h_i + (uint32_t)(32 + (it & 31)) * (B * 4), -lg);
+    }
+    __syncthreads();
+  }
+  const long long t1 = clock64();
+  if (tid == 0 && blockIdx.x == 0) cycles[0] = t1 - t0;
+  if (q == 0) { ab_out[blockIdx.x * 128 + i] = a_new; ab_out[blockIdx.x * 128 + 64 + i] = b_new + hist[1][5][i]; }
+}
 }  // namespace
 }  // namespace kccot
 
@@ -78,4 +162,12 @@ extern "C" int kccot_debug_tma_stream(const float* x, int rows, long long K, int
                                                                                 prefetch_dist, sink);
   KCCOT_LAUNCH_CHECK();
   return KCCOT_OK;
+}
+
+extern "C" int kccot_debug_matvec_probe(int lpr, int iters, const float* C, long long* cycles, float* ab_out, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (lpr == 1) matvec_probe_kernel<1><<<3, 64, 0, st>>>(C, iters, cycles, ab_out);
+  else if (lpr == 2) matvec_probe_kernel<2><<<3, 128, 0, st>>>(C, iters, cycles, ab_out);
+  else matvec_probe_kernel<4><<<3, 256, 0, st>>>(C, iters, cycles, ab_out);
+  return (int)cudaGetLastError();
 }

@@ -227,8 +227,8 @@ __global__ void __launch_bounds__(4 * 4 * EPT) sinkhorn_fwd_small_kernel(
   const int ip = pad_index<EPT>(ic);                            // padded slot of row / column i
   const uint32_t as_q = pin_u32(static_cast<uint32_t>(__cvta_generic_to_shared(as)) + q * (EPT + 4) * 4);
   const uint32_t bs_q = pin_u32(static_cast<uint32_t>(__cvta_generic_to_shared(bs)) + q * (EPT + 4) * 4);
-  const uint32_t bad_a = pin_u32(static_cast<uint32_t>(__cvta_generic_to_shared(&bad_flag)));
   const uint32_t bs_i = pin_u32(static_cast<uint32_t>(__cvta_generic_to_shared(&bs[ip])));
+  const uint32_t bad_a = pin_u32(static_cast<uint32_t>(__cvta_generic_to_shared(&bad_flag)));
   for (int t = tid; t < BM; t += blockDim.x) { urow(0)[t] = 0.f; vrow(0)[t] = 0.f; }
   for (int t = tid; t < BMP; t += blockDim.x) { as[t] = 0.f; bs[t] = 0.f; }
   if (!HS && tid < B) { uh[tid] = 0.f; vh[tid] = 0.f; }
@@ -262,19 +262,22 @@ __global__ void __launch_bounds__(4 * 4 * EPT) sinkhorn_fwd_small_kernel(
       // 8th iteration carries the test (a reducing barrier in place of the plain one); the other seven
       // run in an inner loop with nothing but the two mat-vecs between barriers (a per-iteration test,
       // even off the critical path, cost 65-120 ns of the ~390 ns iteration in control instructions).
-      // Returns 0: done, 1: guard flag seen (nothing written), 2: fixed point reached.
+      // The range guard rides on the same barrier: plain iterations carry no test at all (inf / NaN from a
+      // scaling that left the fp32 range are sticky, so the next tested iteration sees them); a failed test
+      // rolls back to the last tested iteration and redoes the block in the log domain.  (A flag load +
+      // branch in every iteration was ~40 cycles on the critical path: the bare loop of
+      // scripts/matvec_probe.py runs in 569 cycles, this one ran in 800.)
+      // Returns 0: continue, 1: a scaling left the safe range, 2: fixed point reached.
       float unew = 0.f, vnew = 0.f;
       auto iteration = [&](auto check_tag) -> int {
         constexpr bool kCheck = decltype(check_tag)::value;
         const float s = dot_slice<EPT>(Kr, bs_q);
-        if (lds_flag(bad_a)) return 1;                    // set during iteration it-1: rolled back below
         const float a_new = two_ahat * fast_rcp(s);       // critical path first
         unew = ahat + alpha - fast_log2(s);
         if (owner) {
           as[ip] = a_new;
           urow(it + 1)[i] = unew;
           if (!HS) uh[(long long)(it + 1) * B + i] = unew;
-          if (!(s > kLo && s < kHi)) sts_flag(bad_a, 1);
         }
         __syncthreads();
         const float t = dot_slice<EPT>(Kc, as_q);
@@ -286,23 +289,27 @@ __global__ void __launch_bounds__(4 * 4 * EPT) sinkhorn_fwd_small_kernel(
           bs[ip] = b_new;
           vrow(it + 1)[i] = vnew;
           if (!HS) vh[(long long)(it + 1) * B + i] = vnew;
-          if (!(t > kLo && t < kHi)) sts_flag(bad_a, 1);
+          if (kCheck && !(s > kLo && s < kHi && t > kLo && t < kHi)) sts_flag(bad_a, 1);
         }
         if (!kCheck) {
           __syncthreads();
           return 0;
         }
+        // (__syncthreads_or returns a truth value, not the OR of the arguments: the rare range failure goes
+        //  through the shared flag, the fixed-point vote through the barrier)
         const int fixed = __syncthreads_and((i >= B) | (b_new == b_old));
-        return (fixed && lds_flag(bad_a) == 0) ? 2 : 0;
+        if (lds_flag(bad_a) != 0) return 1;
+        return fixed ? 2 : 0;
       };
-      bool leave = false;
-      while (it < first_check && !leave) {
+      while (it < first_check) {
+        const int block_start = it;
         const int plain_end = it + min(first_check - it, 8) - 1;
-        for (; it < plain_end; ++it)
-          if (iteration(std::false_type{})) { leave = true; break; }
-        if (leave) break;
+        for (; it < plain_end; ++it) iteration(std::false_type{});
         const int rc = iteration(std::true_type{});
-        if (rc == 1) break;
+        if (rc == 1) {                                    // redo this block of iterations in the log domain
+          it = block_start + 1;
+          break;
+        }
         if (rc == 2) {                                    // rows >= it + 1 are all equal
           if (owner)
             for (int r = it + 2; r <= first_check; ++r) {
