@@ -395,6 +395,53 @@ def test_smoothing_shapes(shape):
         assert rel_l2(gx.cpu().numpy(), rg) < GRAD_TOL, (mode, shape)
 
 
+@pytest.mark.parametrize("kernel", ["none", "1d", "3d"])
+def test_training_step_closures(kernel):
+    """kernel_train.py:219-292 with stub networks (kccotgan_b200.train_step): the loss the generator step
+    sees equals the fp64 oracle on the same tensors, both steps update exactly the parameters the
+    reference updates, and everything stays finite over a few iterations."""
+    from kccotgan_b200 import gan_utils
+    from kccotgan_b200.data_utils import KernelSmoothing
+    from kccotgan_b200.train_step import StubDiscriminator, StubGenerator, make_training_steps
+    from oracle import closed_form as cf
+    B, H, T, ctx, W, C = 8, 16, 6, 2, 16, 3
+    torch.manual_seed(5)
+    gen = StubGenerator(T - ctx, C).cuda()
+    dh, dm = StubDiscriminator(H, W, C).cuda(), StubDiscriminator(H, W, C).cuda()
+    disc_step, gen_step = make_training_steps(gen, dh, dm, B, kernel_choice=kernel, gen_lr=1e-2, disc_lr=1e-2)
+    x = torch.rand(B, H, T, W, C, device="cuda")
+    real_in, real_pred = x[:, :, :ctx], x[:, :, ctx:]
+    # the loss of the first generator forward against the oracle on the very same tensors
+    with torch.no_grad():
+        z = torch.randn(B, gen.z_dim, device="cuda")
+        fake = torch.cat((real_in, gen(real_in, z)), dim=2)
+        real = x
+        ks = KernelSmoothing(6, 6)
+        if kernel == "1d":
+            real, fake = ks.temporal_convolution(real, 5.0), ks.temporal_convolution(fake, 5.0)
+        elif kernel == "3d":
+            real, fake = ks.gaussian_convolution3D(real, 5.0), ks.gaussian_convolution3D(fake, 5.0)
+        hf, hr, mr, mf = dh(fake), dh(real), dm(real), dm(fake)
+        loss = gan_utils.compute_sinkhorn_loss(real, fake, 1 / 15, 0.8, 100, hf, mr, hr, mf, video=True)
+        a = [t.cpu().numpy().astype(np.float64) for t in (real, fake, hf, mr, hr, mf)]
+        ref, _, det = cf.compute_sinkhorn_loss(a[0], a[1], 1 / 15, 0.8, 100, a[2], a[3], a[4], a[5], grad=True)
+        scale = max(abs(det["loss_xy"]), abs(det["loss_xx"]), abs(det["loss_yy"]))
+        assert abs(float(loss) - ref) <= LOSS_TOL * scale
+    before = [p.detach().clone() for m in (gen, dh, dm) for p in m.parameters()]
+    ngen = len(list(gen.parameters()))
+    pm = disc_step(real_in, real_pred, 5.0)
+    after_d = [p.detach().clone() for m in (gen, dh, dm) for p in m.parameters()]
+    assert all(torch.equal(b, a) for b, a in zip(before[:ngen], after_d[:ngen]))          # generator untouched (:252-255)
+    assert all(not torch.equal(b, a) for b, a in zip(before[ngen:], after_d[ngen:]))      # both discriminators moved
+    loss = gen_step(real_in, real_pred, 5.0)
+    after_g = [p.detach().clone() for m in (gen, dh, dm) for p in m.parameters()]
+    assert all(not torch.equal(b, a) for b, a in zip(after_d[:ngen], after_g[:ngen]))     # generator moved (:289-291)
+    assert all(torch.equal(b, a) for b, a in zip(after_d[ngen:], after_g[ngen:]))
+    for _ in range(3):
+        pm, loss = disc_step(real_in, real_pred, 5.0), gen_step(real_in, real_pred, 5.0)
+    assert np.isfinite(float(pm)) and np.isfinite(float(loss))                             # kernel_train.py:323
+
+
 def test_errors_raise(gu):
     x = torch.rand(8, 4, 16, device="cuda")
     with pytest.raises(ValueError):
