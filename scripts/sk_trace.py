@@ -1,5 +1,14 @@
 """Phase timeline of the small Sinkhorn kernels (clock64 stamps of CTA 0).  Needs a library built with
--DKCCOT_SK_TRACE:  KCCOT_LIB_PATH=<that .so> python scripts/sk_trace.py [B] [L]"""
+-DKCCOT_SK_TRACE, e.g. (after `python -m kccotgan_b200.build`):
+
+  F="-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC --expt-relaxed-constexpr"
+  mkdir -p trace_build
+  nvcc $F -DKCCOT_SK_TRACE -c kccotgan_b200/csrc/sinkhorn_small.cu -o trace_build/sinkhorn_small.o
+  nvcc -shared -o trace_build/libkccot.so $(ls kccotgan_b200/csrc/build/*.o | grep -v sinkhorn_small.o) \
+       trace_build/sinkhorn_small.o -lcudart
+  KCCOT_LIB_PATH=trace_build/libkccot.so python scripts/sk_trace.py [B] [L]
+
+(with programmatic dependent launch the backward's first phase includes its wait for the forward kernel)"""
 import ctypes, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
