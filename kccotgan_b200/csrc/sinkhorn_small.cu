@@ -22,6 +22,8 @@
 // back one iteration and continues, for the rest of the solve, with the plain log-domain updates with
 // max subtraction — the reference's formulation.  The backward switches to direct exponentials before
 // any rank-one factor would leave 2^+-60.
+#include <stdlib.h>
+
 #include <type_traits>
 
 #include "common.cuh"
@@ -46,19 +48,28 @@ constexpr float kLo = 8.0e-28f;    // ~2^-90
 constexpr float kHi = 1.2e27f;     // ~2^90
 constexpr float kExpLim = 60.f;    // |log2| allowed for a backward rank-one factor
 
-__device__ __forceinline__ float quad_sum(float v) {
-  v += __shfl_xor_sync(0xffffffffu, v, 1);
-  v += __shfl_xor_sync(0xffffffffu, v, 2);
+// Lanes per row (and per column): a row of the B x B problem is split over LPR adjacent lanes, EPT elements
+// each.  EPT = 8 / 16: four lanes (B <= 32 / 64); EPT = 32: two lanes (B <= 64) — one shuffle instead of two
+// and a 4-warp barrier instead of an 8-warp one: 478 against 569 cycles per iteration in
+// scripts/matvec_probe.py.
+__host__ __device__ constexpr int lpr_of(int ept) { return ept == 32 ? 2 : 4; }
+
+template <int LPR>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int o = 1; o < LPR; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
-__device__ __forceinline__ float quad_max(float v) {
-  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
-  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+template <int LPR>
+__device__ __forceinline__ float group_max(float v) {
+#pragma unroll
+  for (int o = 1; o < LPR; o <<= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
-__device__ __forceinline__ float quad_min(float v) {
-  v = fminf(v, __shfl_xor_sync(0xffffffffu, v, 1));
-  v = fminf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+template <int LPR>
+__device__ __forceinline__ float group_min(float v) {
+#pragma unroll
+  for (int o = 1; o < LPR; o <<= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
 __device__ __forceinline__ float fast_rcp(float x) {
@@ -83,7 +94,8 @@ __device__ __forceinline__ float block_reduce(float v, float* red, bool is_min) 
 template <int EPT>
 __device__ __forceinline__ float load_slices(const float* __restrict__ Cn, int B, float kscale, float* red,
                                              float (&Cr)[EPT], float (&Cc)[EPT]) {
-  const int i = threadIdx.x >> 2, q = threadIdx.x & 3;
+  constexpr int LPR = lpr_of(EPT);
+  const int i = threadIdx.x / LPR, q = threadIdx.x % LPR;
   float mn = kBig;
 #pragma unroll
   for (int e = 0; e < EPT; ++e) {
@@ -111,14 +123,14 @@ __device__ __forceinline__ float lse_update(const float (&Cs)[EPT], const float*
     t[e] = (Cs[e] < kBig) ? pot[e] - Cs[e] : -kBig;      // padded entries: their potentials are unset
     m = fmaxf(m, t[e]);
   }
-  m = quad_max(m);
+  m = group_max<lpr_of(EPT)>(m);
   float s0 = 0.f, s1 = 0.f;
 #pragma unroll
   for (int e = 0; e < EPT; e += 2) {
     s0 += fast_exp2(t[e] - m);
     s1 += fast_exp2(t[e + 1] - m);
   }
-  return ahat - (m + fast_log2(quad_sum(s0 + s1)));
+  return ahat - (m + fast_log2(group_sum<lpr_of(EPT)>(s0 + s1)));
 }
 
 // Vectors that every thread reads a 16-element slice of are stored PADDED: chunk q starts at
@@ -176,7 +188,7 @@ __device__ __forceinline__ float dot_slice(const float (&Ks)[EPT], uint32_t sadd
     s2 = fmaf(Ks[e + 2], b.z, s2);
     s3 = fmaf(Ks[e + 3], b.w, s3);
   }
-  return quad_sum((s0 + s1) + (s2 + s3));
+  return group_sum<lpr_of(EPT)>((s0 + s1) + (s2 + s3));
 }
 }  // namespace
 
@@ -184,19 +196,20 @@ __device__ __forceinline__ float dot_slice(const float (&Ks)[EPT], uint32_t sadd
 // is written to global memory once at the end; HS = false (history too large): one global store per
 // half-iteration.
 template <int EPT, bool HS>
-__global__ void __launch_bounds__(4 * 4 * EPT) sinkhorn_fwd_small_kernel(
+__global__ void __launch_bounds__(lpr_of(EPT) * lpr_of(EPT) * EPT) sinkhorn_fwd_small_kernel(
     const float* __restrict__ C, int B, float eps, int L, int Lmin, float thresh, int exit_on_index,
     float* __restrict__ u_hist, float* __restrict__ v_hist, int32_t* __restrict__ nits_out,
     float* __restrict__ cost_out, SinkhornMix mix) {
-  constexpr int BM = 4 * EPT;
-  constexpr int BMP = 4 * (EPT + 4);
+  constexpr int LPR = lpr_of(EPT);
+  constexpr int BM = LPR * EPT;
+  constexpr int BMP = LPR * (EPT + 4);
   extern __shared__ __align__(16) float hist[];         // HS: Uh[L+1][BM] | Vh[L+1][BM]
   __shared__ __align__(16) float us[BM], vs[BM];        // !HS: current log2-domain potentials
   __shared__ __align__(16) float as[BMP], bs[BMP];      // linear scalings a_i, b_j of the fast path (padded)
   __shared__ float red[32];
   __shared__ int stop_flag, bad_flag;
   const int n = blockIdx.x;
-  const int tid = threadIdx.x, i = tid >> 2, q = tid & 3;
+  const int tid = threadIdx.x, i = tid / LPR, q = tid % LPR;
   const int ic = min(i, BM - 1);
   const bool owner = (q == 0) && (i < B);
   const float kscale = kLog2e / eps;
@@ -222,7 +235,7 @@ __global__ void __launch_bounds__(4 * 4 * EPT) sinkhorn_fwd_small_kernel(
     float rm = kBig;
 #pragma unroll
     for (int e = 0; e < EPT; ++e) rm = fminf(rm, Cr[e]);
-    alpha = quad_min(rm);
+    alpha = group_min<LPR>(rm);
   }
   const int ip = pad_index<EPT>(ic);                            // padded slot of row / column i
   const uint32_t as_q = pin_u32(static_cast<uint32_t>(__cvta_generic_to_shared(as)) + q * (EPT + 4) * 4);
@@ -475,14 +488,15 @@ __global__ void __launch_bounds__(4 * 4 * EPT) sinkhorn_fwd_small_kernel(
 // front (51 KB at B=64, L=100) so every step reads its operands with LDS; HS = false (history too
 // large): two rows are staged per step with a register prefetch from L2.
 template <int EPT, bool HS>
-__global__ void __launch_bounds__(4 * 4 * EPT) sinkhorn_bwd_small_kernel(
+__global__ void __launch_bounds__(lpr_of(EPT) * lpr_of(EPT) * EPT) sinkhorn_bwd_small_kernel(
     const float* __restrict__ C, int B, float eps, int L, const float* __restrict__ u_hist,
     const float* __restrict__ v_hist, const int32_t* __restrict__ nits_in, const float* __restrict__ gcost,
     float* __restrict__ Cbar, const int32_t* __restrict__ only_if, SinkhornMix mix) {
   if (only_if != nullptr && only_if[blockIdx.x] == 0) return;     // fallback launch: only the declined problems
-  constexpr int BM = 4 * EPT;
+  constexpr int LPR = lpr_of(EPT);
+  constexpr int BM = LPR * EPT;
   constexpr int PQ = EPT + 4;                           // padded chunk stride (see pad_index)
-  constexpr int BMP = 4 * PQ;
+  constexpr int BMP = LPR * PQ;
   extern __shared__ __align__(16) float hist[];         // HS: Uh[nits+1][BMP] | Vh[nits+1][BMP]
   __shared__ __align__(16) float Us[2][BMP], Vs[2][BMP];  // !HS: staged u^k / v^k, v^{k-1}
   __shared__ __align__(16) float un_s[BMP], vn_s[BMP];  // final potentials (absorption reference)
@@ -491,7 +505,7 @@ __global__ void __launch_bounds__(4 * 4 * EPT) sinkhorn_bwd_small_kernel(
   __shared__ float red[32];
   __shared__ int slow_flag, k_slow;
   const int n = blockIdx.x;
-  const int tid = threadIdx.x, i = tid >> 2, q = tid & 3;
+  const int tid = threadIdx.x, i = tid / LPR, q = tid % LPR;
   const bool owner = (q == 0) && (i < B);
   const int ip = pad_index<EPT>(min(i, BM - 1));        // padded slot of row / column i
   const int tp = pad_index<EPT>(min(tid, BM - 1));      // padded slot of element tid (loader threads)
@@ -619,8 +633,8 @@ __global__ void __launch_bounds__(4 * 4 * EPT) sinkhorn_bwd_small_kernel(
       rv = fmaf(Kc[e], ce_c, rv);
       Gc[e] = 0.f;
     }
-    ru = quad_sum(ru);
-    rv = quad_sum(rv);
+    ru = group_sum<LPR>(ru);
+    rv = group_sum<LPR>(rv);
     if (owner) {
       ub[ip] = ru;
       vb[ip] = rv;
@@ -661,7 +675,7 @@ __global__ void __launch_bounds__(4 * 4 * EPT) sinkhorn_bwd_small_kernel(
         a0 += t0 + t2;
         a1 += t1 + t3;
       }
-      const float ubn = ub_carry - quad_sum((a0 + a1) * fa);
+      const float ubn = ub_carry - group_sum<LPR>((a0 + a1) * fa);
       ub_carry = 0.f;
       if (owner) {
         sts_f32(ub_i, ubn);
@@ -682,7 +696,7 @@ __global__ void __launch_bounds__(4 * 4 * EPT) sinkhorn_bwd_small_kernel(
         c0 += t0 + t2;
         c1 += t1 + t3;
       }
-      const float vbn = -quad_sum((c0 + c1) * fb);
+      const float vbn = -group_sum<LPR>((c0 + c1) * fb);
       if (owner) {
         sts_f32(vb_i, vbn);
         sts_f32(gb_i, fb * vbn);
@@ -737,7 +751,7 @@ __global__ void __launch_bounds__(4 * 4 * EPT) sinkhorn_bwd_small_kernel(
         }
         part = a0;
       }
-      const float acc = quad_sum(part);
+      const float acc = group_sum<LPR>(part);
       if (owner) {
         const float ubn = ((k == nits) ? lds_f32(ub_i) : 0.f) - acc;
         sts_f32(ub_i, ubn);
@@ -777,7 +791,7 @@ __global__ void __launch_bounds__(4 * 4 * EPT) sinkhorn_bwd_small_kernel(
         }
         part = a0;
       }
-      const float acc = quad_sum(part);
+      const float acc = group_sum<LPR>(part);
       if (owner) {
         sts_f32(vb_i, -acc);
         sts_f32(gb_i, fb * (-acc));          // factor of the next row phase: v^{k-1} here is its v^k
@@ -837,10 +851,16 @@ __global__ void __launch_bounds__(4 * 4 * EPT) sinkhorn_bwd_small_kernel(
   SK_STAMP(1, 7);
 }
 
+// forward, 32 < B <= 64: two lanes per row by default; KCCOT_SK_LANES=4 selects the four-lane mapping (A/B timing)
+static bool four_lanes() {
+  static const bool v = [] { const char* e = getenv("KCCOT_SK_LANES"); return e && atoi(e) == 4; }();
+  return v;
+}
+
 template <int EPT>
 static int launch_fwd_t(const float* C, int nsolve, int B, float eps, int L, int Lmin, float thresh, int exit_on_index,
                         float* u_hist, float* v_hist, int32_t* nits, float* cost, int threads, cudaStream_t st, SinkhornMix mix) {
-  const size_t hist_bytes = (size_t)2 * (L + 1) * 4 * EPT * sizeof(float);
+  const size_t hist_bytes = (size_t)2 * (L + 1) * lpr_of(EPT) * EPT * sizeof(float);
   if (hist_bytes <= 160 * 1024) {
     static bool attr = false;
     if (!attr) {
@@ -861,17 +881,19 @@ static int launch_fwd_t(const float* C, int nsolve, int B, float eps, int L, int
 int launch_sinkhorn_fwd_small(const float* C, int nsolve, int B, float eps, int L, int Lmin, float thresh,
                               int exit_on_index, float* u_hist, float* v_hist, int32_t* nits, float* cost,
                               cudaStream_t st, SinkhornMix mix) {
-  const int threads = ((4 * B + 31) / 32) * 32;
+  const int t4 = ((4 * B + 31) / 32) * 32, t2 = ((2 * B + 31) / 32) * 32;
   if (B <= 32)
-    return launch_fwd_t<8>(C, nsolve, B, eps, L, Lmin, thresh, exit_on_index, u_hist, v_hist, nits, cost, threads, st, mix);
-  return launch_fwd_t<16>(C, nsolve, B, eps, L, Lmin, thresh, exit_on_index, u_hist, v_hist, nits, cost, threads, st, mix);
+    return launch_fwd_t<8>(C, nsolve, B, eps, L, Lmin, thresh, exit_on_index, u_hist, v_hist, nits, cost, t4, st, mix);
+  if (four_lanes())
+    return launch_fwd_t<16>(C, nsolve, B, eps, L, Lmin, thresh, exit_on_index, u_hist, v_hist, nits, cost, t4, st, mix);
+  return launch_fwd_t<32>(C, nsolve, B, eps, L, Lmin, thresh, exit_on_index, u_hist, v_hist, nits, cost, t2, st, mix);
 }
 
 template <int EPT>
 static int launch_bwd_t(const float* C, int nsolve, int B, float eps, int L, const float* u_hist, const float* v_hist,
                         const int32_t* nits, const float* gcost, float* Cbar, const int32_t* only_if, int threads,
                         cudaStream_t st, SinkhornMix mix) {
-  const size_t hist_bytes = (size_t)2 * (L + 1) * 4 * (EPT + 4) * sizeof(float);
+  const size_t hist_bytes = (size_t)2 * (L + 1) * lpr_of(EPT) * (EPT + 4) * sizeof(float);
   if (hist_bytes <= 160 * 1024) {
     static size_t attr = 0;
     if (hist_bytes > attr) {
@@ -879,7 +901,7 @@ static int launch_bwd_t(const float* C, int nsolve, int B, float eps, int L, con
                                       (int)(160 * 1024)));
       attr = 160 * 1024;
     }
-    const size_t tile_bytes = (size_t)(4 * EPT) * (4 * EPT + 1) * sizeof(float);      // Cbar transposition tile of the epilogue
+    const size_t tile_bytes = (size_t)(lpr_of(EPT) * EPT) * (lpr_of(EPT) * EPT + 1) * sizeof(float);      // Cbar transposition tile of the epilogue
     KCCOT_CUDA(launch_pdl(sinkhorn_bwd_small_kernel<EPT, true>, dim3(nsolve), dim3(threads),
                           hist_bytes > tile_bytes ? hist_bytes : tile_bytes, st, C, B, eps, L, u_hist, v_hist, nits, gcost,
                           Cbar, only_if, mix));
@@ -894,9 +916,12 @@ static int launch_bwd_t(const float* C, int nsolve, int B, float eps, int L, con
 int launch_sinkhorn_bwd_small(const float* C, int nsolve, int B, float eps, int L, const float* u_hist,
                               const float* v_hist, const int32_t* nits, const float* gcost, float* Cbar,
                               const int32_t* only_if, cudaStream_t st, SinkhornMix mix) {
-  const int threads = ((4 * B + 31) / 32) * 32;
-  if (B <= 32) return launch_bwd_t<8>(C, nsolve, B, eps, L, u_hist, v_hist, nits, gcost, Cbar, only_if, threads, st, mix);
-  return launch_bwd_t<16>(C, nsolve, B, eps, L, u_hist, v_hist, nits, gcost, Cbar, only_if, threads, st, mix);
+  // always four lanes per row: the backward carries three times the arithmetic of the forward per element
+  // (rank-one accumulation of Cbar), and with two lanes its single warp per scheduler becomes issue-bound
+  // (measured: backward chain 72 -> 87 us), while the forward gains (33 -> 28 us)
+  const int t4 = ((4 * B + 31) / 32) * 32;
+  if (B <= 32) return launch_bwd_t<8>(C, nsolve, B, eps, L, u_hist, v_hist, nits, gcost, Cbar, only_if, t4, st, mix);
+  return launch_bwd_t<16>(C, nsolve, B, eps, L, u_hist, v_hist, nits, gcost, Cbar, only_if, t4, st, mix);
 }
 
 }  // namespace kccot
