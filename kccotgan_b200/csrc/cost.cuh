@@ -15,6 +15,7 @@ struct CostBlock {
   long long C_prob_stride;
   int Bx, By, zero_diag;
   int sym;                 // partials hold only hi.lo^T of the cross terms: C_ij = (P_ij + P_ji) / 2 (tensor-core path)
+  int tiled;               // tensor-core partial layout part[p][16 x 16 tiles of 8 x 8][ks][64] (sym implied)
 };
 struct CostBlocks {
   CostBlock b[3];

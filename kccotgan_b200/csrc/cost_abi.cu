@@ -75,7 +75,7 @@ int kccot_cost_fwd(const float* x, const float* y, int nprob, int Bx, int By, lo
     if (int rc = launch_sqdist_partials_tc(x, same ? nullptr : y, nprob, Bx, same ? 0 : By, K, ks, kbps, (float*)ws, st))
       return rc;
     b.prob_stride = (long long)ks * kTcTile; b.ks_stride = kTcTile; b.ld = 128; b.nks = ks;
-    b.row_off = 0; b.col_off = same ? 0 : Bx; b.sym = 1;
+    b.row_off = 0; b.col_off = same ? 0 : Bx; b.sym = 1; b.tiled = 1;
   } else {
     int ks;
     long long slab;
@@ -137,7 +137,7 @@ int mixed_cost_fwd_impl(const float* real, const float* fake, int nprob, int B, 
     for (int q = 0; q < 3; ++q) {
       CostBlock& b = blocks.b[q];
       b.part = (const float*)ws; b.prob_stride = (long long)ks * kTcTile; b.ks_stride = kTcTile; b.ld = 128;
-      b.nks = ks; b.row_off = roff[q]; b.col_off = coff[q]; b.sym = 1;
+      b.nks = ks; b.row_off = roff[q]; b.col_off = coff[q]; b.sym = 1; b.tiled = 1;
     }
   } else {
     int ks;

@@ -162,6 +162,99 @@ __global__ void __launch_bounds__(128 * FGmax) cost_finalize_kernel(CostBlocks b
   }
 }
 
+// Same result for the tensor-core partial layout part[p][16 x 16 tiles][ks][8][8]: the nks partials of an
+// output tile (and of its mirror tile) are two contiguous streams of nks x 256 bytes, read with coalesced
+// 16-byte loads in two batches; the martingale operands are staged in shared memory by the same threads, so
+// the kernel is two L2 round trips deep instead of eight (the scattered-sector version above took 11 us in
+// the evaluation chain).  512 threads: 256 on the tile as stored, 256 on the mirror tile; thread = (k-slab
+// group g of 16, 16-byte slot q of 16).
+constexpr int kFinMaxTJ = 256;      // (T-1)*J limit of the staged martingale operands
+
+__global__ void __launch_bounds__(512, 2) cost_finalize_tiled_kernel(CostBlocks blocks, int T, int J, float s) {
+  __shared__ double red[2][16][16][4];       // [as stored / mirror][k-slab group][slot][component]
+  __shared__ double redm[8][FT * FT];        // martingale partial sums
+  __shared__ float hs[FT][kFinMaxTJ], dms[FT][kFinMaxTJ];
+  pdl_wait();                                // the partial tiles come from the kernel before
+  pdl_launch_dependents();
+  if (blocks.zero != nullptr && blockIdx.x == 0 && blockIdx.z == 0 && threadIdx.x == 0) blocks.zero[blockIdx.y] = 0;
+  const CostBlock& b = blocks.b[blockIdx.z];
+  const int tiles_j = b.By / FT;
+  const int p = blockIdx.y;
+  const int ti = blockIdx.x / tiles_j, tj = blockIdx.x % tiles_j;
+  const int i0 = ti * FT, j0 = tj * FT;
+  const int tid = threadIdx.x, half = tid >> 8, t = tid & 255, g = t >> 4, q = t & 15;
+  const int tj1 = (T - 1) * J, TJ = T * J;
+  const int tr = (b.row_off + i0) >> 3, tc = (b.col_off + j0) >> 3;
+  const int tile = half ? tc * 16 + tr : tr * 16 + tc;
+  const float4* pp = reinterpret_cast<const float4*>(b.part + ((long long)p * 256 + tile) * b.nks * 64) + q;
+  // ---- two batches of coalesced loads; the staging loads of the martingale operands go out in between ----
+  constexpr int kBatch = 5;
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  float4 v[kBatch];
+#pragma unroll
+  for (int u = 0; u < kBatch; ++u) {
+    const int ks = g + u * 16;
+    v[u] = (ks < b.nks) ? pp[ks * 16] : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  // h rows i0.., DeltaM rows j0.., columns [c0, c0 + n) -> shared memory
+  auto stage = [&](const float* h, const float* M, int c0, int n) {
+    for (int e = tid; e < FT * n; e += 512) {
+      const int r = e / n, c = e - r * n;
+      const float* Mr = M + ((long long)p * b.By + j0 + r) * TJ + c0 + c;
+      hs[r][c] = h[((long long)p * b.Bx + i0 + r) * TJ + c0 + c];
+      dms[r][c] = Mr[J] - Mr[0];
+    }
+  };
+  const int n_first = min(tj1, kFinMaxTJ);
+  if (b.h1) stage(b.h1, b.M1, 0, n_first);
+#pragma unroll
+  for (int u = 0; u < kBatch; ++u) { a0 += (double)v[u].x; a1 += (double)v[u].y; a2 += (double)v[u].z; a3 += (double)v[u].w; }
+  for (int k0 = kBatch * 16; k0 < b.nks; k0 += kBatch * 16) {
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u) {
+      const int ks = k0 + g + u * 16;
+      v[u] = (ks < b.nks) ? pp[ks * 16] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u) { a0 += (double)v[u].x; a1 += (double)v[u].y; a2 += (double)v[u].z; a3 += (double)v[u].w; }
+  }
+  red[half][g][q][0] = a0; red[half][g][q][1] = a1; red[half][g][q][2] = a2; red[half][g][q][3] = a3;
+  // ---- martingale term: sum_pairs h_row . DeltaM_col out of shared memory ---------------------------
+  const int e = tid & 63, part = tid >> 6;                  // 8 parts x 64 elements
+  const int er = e >> 3, ec = e & 7;
+  double am = 0.0;
+  for (int pr = 0; pr < 2; ++pr) {
+    const float* h = pr ? b.h2 : b.h1;
+    const float* M = pr ? b.M2 : b.M1;
+    if (h == nullptr) continue;
+    for (int c0 = 0; c0 < tj1; c0 += kFinMaxTJ) {
+      const int n = min(kFinMaxTJ, tj1 - c0);
+      if (pr == 1 || c0 > 0) {
+        __syncthreads();                                     // previous chunk consumed
+        stage(h, M, c0, n);
+      }
+      __syncthreads();
+      float a = 0.f;
+      for (int c = part; c < n; c += 8) a = fmaf(hs[er][c], dms[ec][c], a);
+      am += (double)a;
+    }
+  }
+  redm[part][e] = am;
+  __syncthreads();
+  if (tid < FT * FT) {
+    const int r = tid >> 3, c = tid & 7;
+    double d = 0.0;
+    if (!(b.zero_diag && i0 + r == j0 + c)) {
+      const int qd = r * 2 + (c >> 2), cd = c & 3;           // (r, c) in the tile as stored
+      const int qm = c * 2 + (r >> 2), cm = r & 3;           // (c, r) in the mirror tile
+      for (int gg = 0; gg < 16; ++gg) d += red[0][gg][qd][cd] + red[1][gg][qm][cm];   // fixed order: deterministic
+      d *= 0.5;
+    }
+    for (int gg = 0; gg < 8; ++gg) d += redm[gg][tid];
+    b.C[(long long)p * b.C_prob_stride + (long long)(i0 + r) * b.By + j0 + c] = (float)((double)s * d);
+  }
+}
+
 int launch_cost_finalize(const CostBlocks& blocks, int nblocks, int nprob, int T, int J, float s,
                          cudaStream_t st) {
   int tiles = 0, nks = 1;
@@ -171,6 +264,11 @@ int launch_cost_finalize(const CostBlocks& blocks, int nblocks, int nprob, int T
     nks = max(nks, b.nks);
   }
   const int G = nks >= 64 ? 8 : nks >= 16 ? 4 : nks >= 4 ? 2 : 1;
+  bool all_tiled = true;
+  for (int i = 0; i < nblocks; ++i) {
+    const CostBlock& b = blocks.b[i];
+    if (!b.tiled || b.Bx % FT || b.By % FT || b.row_off % FT || b.col_off % FT) all_tiled = false;
+  }
   for (int p0 = 0; p0 < nprob; p0 += 65535) {     // grid.y limit
     CostBlocks bl = blocks;
     const int np = min(65535, nprob - p0);
@@ -182,7 +280,11 @@ int launch_cost_finalize(const CostBlocks& blocks, int nblocks, int nprob, int T
       if (bl.b[i].h2) { bl.b[i].h2 += (long long)p0 * bl.b[i].Bx * T * J; bl.b[i].M2 += (long long)p0 * bl.b[i].By * T * J; }
     }
     dim3 grid((unsigned)tiles, (unsigned)np, (unsigned)nblocks);
-    KCCOT_CUDA(launch_pdl(cost_finalize_kernel, grid, dim3(128 * G), (size_t)0, st, bl, T, J, s));
+    if (all_tiled) {
+      KCCOT_CUDA(launch_pdl(cost_finalize_tiled_kernel, grid, dim3(512), (size_t)0, st, bl, T, J, s));
+    } else {
+      KCCOT_CUDA(launch_pdl(cost_finalize_kernel, grid, dim3(128 * G), (size_t)0, st, bl, T, J, s));
+    }
     KCCOT_LAUNCH_CHECK();
   }
   return KCCOT_OK;

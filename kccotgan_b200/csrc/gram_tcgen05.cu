@@ -215,7 +215,10 @@ sqdist_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
       const int row = quad * 32 + lane;
       const int half = cw >> 2;                   // columns [64*half, 64*half + 64)
       const float nr = (row < R) ? S.nrm[row] : 0.f;
-      float* out = part + ((long long)w * kRows + row) * kRows;
+      // tile-major layout: the ksplit partials of one 8 x 8 output tile are contiguous (ksplit x 256 bytes),
+      // so cost_finalize_tiled_kernel reads them as one coalesced stream
+      const int pw = w / ksplit;
+      float* out = part + ((long long)pw * 256 + (row >> 3) * 16) * ksplit * 64 + (long long)ks * 64 + (row & 7) * 8;
 #pragma unroll
       for (int cc = 0; cc < 2; ++cc) {
         const int c0 = half * 64 + cc * 32;
@@ -241,7 +244,8 @@ sqdist_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
               o.y = nr + S.nrm[min(c0 + j + 1, kRows - 1)] - 2.f * d[j + 1];
               o.z = nr + S.nrm[min(c0 + j + 2, kRows - 1)] - 2.f * d[j + 2];
               o.w = nr + S.nrm[min(c0 + j + 3, kRows - 1)] - 2.f * d[j + 3];
-              if (c0 + j < R) *reinterpret_cast<float4*>(out + c0 + j) = o;
+              if (c0 + j < R)
+                *reinterpret_cast<float4*>(out + (long long)((c0 + j) >> 3) * ksplit * 64 + ((c0 + j) & 7)) = o;
             }
           }
         }
