@@ -105,3 +105,29 @@ def test_filter_matrix_matches_oracle():
         assert np.allclose(A.sum(axis=1), 1.0, atol=1e-6)
     with pytest.raises(ValueError):
         ks._filter_matrix(3, 3, 5.0, "cpu")
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/kccot.h is the drop-in boundary: it must compile as C (no C++ or torch types) and every
+    prototype must match the ctypes table used by the Python host (count and pointer-vs-scalar kinds)."""
+    import re
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = os.path.join(root, "include", "kccot.h")
+    src = tmp_path / "t.c"
+    src.write_text('#include "kccot.h"\nint (*probe)(void) = kccot_version;\nint main(void) { return probe == 0; }\n')
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.dirname(hdr), str(src)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    from kccotgan_b200 import _lib
+    text = re.sub(r"/\*.*?\*/", "", open(hdr).read(), flags=re.S)
+    protos = re.findall(r"\b(kccot_\w+)\s*\(([^;{]*?)\)\s*;", text)
+    assert protos
+    for name, args in protos:
+        assert name in _lib.SIGNATURES, name
+        args = [a.strip() for a in args.split(",") if a.strip() and a.strip() != "void"]
+        _, ctypes_args = _lib.SIGNATURES[name]
+        assert len(args) == len(ctypes_args), (name, len(args), len(ctypes_args))
+        for a, ct in zip(args, ctypes_args):
+            is_ptr = "*" in a
+            assert is_ptr == (ct is _lib._P), (name, a, ct)
