@@ -131,3 +131,27 @@ def test_header_is_plain_c(tmp_path):
         for a, ct in zip(args, ctypes_args):
             is_ptr = "*" in a
             assert is_ptr == (ct is _lib._P), (name, a, ct)
+
+
+def _build_c_demo(tmp_path):
+    import subprocess
+    root = ROOT
+    exe = str(tmp_path / "mixed_loss_demo")
+    libdir = os.path.join(root, "kccotgan_b200")
+    cmd = ["gcc", "-O2", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(root, "include"), "-I", "/usr/local/cuda/include",
+           os.path.join(root, "examples", "mixed_loss_demo.c"), "-L", libdir, "-lkccot", "-L", "/usr/local/cuda/lib64", "-lcudart",
+           "-Wl,-rpath," + libdir, "-o", exe]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+def test_c_demo_links_and_fails_loudly_without_gpu(lib, tmp_path):
+    """examples/mixed_loss_demo.c (plain C, no PyTorch) links against libkccot.so; without a device it must
+    exit with an error instead of computing anything on the host."""
+    import subprocess
+    exe = _build_c_demo(tmp_path)
+    if torch.cuda.is_available():
+        pytest.skip("covered by the GPU test")
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 2 and "no CUDA device" in r.stderr

@@ -442,6 +442,49 @@ def test_training_step_closures(kernel):
     assert np.isfinite(float(pm)) and np.isfinite(float(loss))                             # kernel_train.py:323
 
 
+def test_c_abi_from_plain_c(gu, tmp_path):
+    """examples/mixed_loss_demo.c drives the C ABI with nothing but the CUDA runtime: its loss, terms and
+    gradient checksums must equal the Python host path on the same (LCG-generated) inputs, and the loss the
+    fp64 oracle."""
+    import subprocess
+    from test_abi import _build_c_demo
+    from oracle import closed_form as cf
+    exe = _build_c_demo(tmp_path)
+    B, T, H, W, C, J = 16, 6, 8, 8, 3, 8
+    r = subprocess.run([exe, str(B), str(T), str(H), str(W), str(C)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = dict()
+    for line in r.stdout.splitlines():
+        w = line.split()
+        if w[0] == "loss":
+            out.update(loss=float(w[1]), xy=float(w[3]), xx=float(w[5]), yy=float(w[7]))
+        elif w[0] == "grad":
+            out["g_" + w[1]] = float(w[2])
+    state = 12345
+    def draw(n, lo, hi):
+        nonlocal state
+        a = np.empty(n, dtype=np.float32)
+        for i in range(n):
+            state = (state * 1664525 + 1013904223) & 0xFFFFFFFF
+            a[i] = np.float32(lo) + (np.float32(hi) - np.float32(lo)) * (np.float32(state >> 8) * np.float32(1.0 / 16777216.0))
+        return a
+    K = T * H * W * C
+    real = draw(B * K, 0, 1).reshape(B, T, H * W * C)
+    fake = draw(B * K, 0, 1).reshape(B, T, H * W * C)
+    hm = [draw(B * T * J, 0.1, 0.9).reshape(B, T, J) for _ in range(4)]
+    leaves = [torch.from_numpy(a).cuda().requires_grad_(True) for a in (real, fake, *hm)]
+    loss = gu.compute_sinkhorn_loss(leaves[0], leaves[1], 1 / 15, 0.8, 100, *leaves[2:], video=False)
+    grads = torch.autograd.grad(loss, leaves)
+    assert abs(out["loss"] - float(loss)) <= 1e-6 * max(abs(out["xy"]), 1.0)
+    for n, g in zip(GRAD_NAMES, grads):
+        flat = g.detach().cpu().numpy().reshape(-1).astype(np.float64)
+        ck = float((flat * (1 + np.arange(flat.size) % 7)).sum())
+        assert abs(out["g_" + n] - ck) <= 1e-5 * (np.abs(flat).sum() * 7 + 1e-12), (n, out["g_" + n], ck)
+    ref, _, det = cf.compute_sinkhorn_loss(real, fake, 1 / 15, 0.8, 100, *hm, grad=True)
+    scale = max(abs(det["loss_xy"]), abs(det["loss_xx"]), abs(det["loss_yy"]))
+    assert abs(out["loss"] - ref) <= LOSS_TOL * scale and abs(out["xy"] - det["loss_xy"]) <= LOSS_TOL * scale
+
+
 def test_errors_raise(gu):
     x = torch.rand(8, 4, 16, device="cuda")
     with pytest.raises(ValueError):
