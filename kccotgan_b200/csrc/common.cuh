@@ -44,6 +44,18 @@ inline void count_launch(int n = 1) { g_launches.fetch_add((unsigned long long)n
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// Function attributes (the opt-in to more than 48 KB of dynamic shared memory) are per DEVICE: a call site
+// keeps one `static size_t cache[kMaxDevices]` and asks here whether the current device still needs
+// cudaFuncSetAttribute for `want` bytes.  (A benign race between host threads costs a redundant call.)
+constexpr int kMaxDevices = 64;
+inline bool smem_attr_needed(size_t (&cache)[kMaxDevices], size_t want) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return true;
+  if (want <= cache[dev]) return false;
+  cache[dev] = want;
+  return true;
+}
+
 // Programmatic dependent launch (sm_90+).  A kernel launched with launch_pdl() may start while the previous
 // kernel of the stream is still running, once every CTA of that kernel has executed pdl_launch_dependents()
 // (or exited); it must execute pdl_wait() before touching anything the previous kernel writes.  Rule used

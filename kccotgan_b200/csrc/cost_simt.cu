@@ -512,11 +512,9 @@ int launch_martingale_jobs(const MartJobs& jobs, int njobs, int nprob, int T, in
     set_error("martingale adjoint: T*J = %d too large (max %d)", TJ, 8 * 256 / MR);
     return KCCOT_EINVAL;
   }
-  static size_t attr = 48 * 1024;
-  if (smem > attr) {
+  static size_t attr[kMaxDevices] = {};
+  if (smem > 48 * 1024 && smem_attr_needed(attr, 200 * 1024))
     KCCOT_CUDA(cudaFuncSetAttribute(martingale_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr = 200 * 1024;
-  }
   dim3 grid((maxrows + MR - 1) / MR, njobs, nprob);
   martingale_bwd_kernel<<<grid, 256, smem, st>>>(jobs, T, J, s);
   KCCOT_LAUNCH_CHECK();

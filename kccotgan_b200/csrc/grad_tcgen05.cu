@@ -444,11 +444,9 @@ static int launch_grad_rows(const CUtensorMap& tmx, const CUtensorMap& tmy, cons
   if (int rc = encode_tmap_3d(&tmo, out, (uint64_t)K, (uint64_t)N, (uint64_t)nprob, (uint64_t)K * 4, (uint64_t)K * 4 * N,
                               kBoxCols, (uint32_t)N))
     return rc;
-  static size_t attr_smem = 0;
-  if (g.smem > attr_smem) {
+  static size_t attr_smem[kMaxDevices] = {};
+  if (smem_attr_needed(attr_smem, g.smem))
     KCCOT_CUDA(cudaFuncSetAttribute(grad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
-    attr_smem = g.smem;
-  }
   const long long ntiles = (K + kCols - 1) / kCols;
   int gx = (int)((num_sms() + nprob - 1) / nprob);
   if (gx > ntiles) gx = (int)ntiles;

@@ -349,11 +349,9 @@ int launch_sqdist_partials_tc(const float* x, const float* y, int nprob, int Bx,
     By = 0;
   }
   const size_t smem = sizeof(Smem) + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static size_t attr_set[kMaxDevices] = {};
+  if (smem_attr_needed(attr_set, smem))
     KCCOT_CUDA(cudaFuncSetAttribute(sqdist_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
   const int grid = min(nprob * ksplit, num_sms());
   sqdist_tc_kernel<<<grid, kThreads, smem, st>>>(tmx, tmy, Bx, By, K, nprob, ksplit, kbps, part);
   KCCOT_LAUNCH_CHECK();

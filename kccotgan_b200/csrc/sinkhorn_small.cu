@@ -914,12 +914,10 @@ static int launch_fwd_t(const float* C, int nsolve, int B, float eps, int L, int
                         float* u_hist, float* v_hist, int32_t* nits, float* cost, int threads, cudaStream_t st, SinkhornMix mix) {
   const size_t hist_bytes = (size_t)2 * (L + 1) * lpr_of(EPT) * EPT * sizeof(float);
   if (hist_bytes <= 160 * 1024) {
-    static bool attr = false;
-    if (!attr) {
+    static size_t attr[kMaxDevices] = {};
+    if (smem_attr_needed(attr, 160 * 1024))
       KCCOT_CUDA(cudaFuncSetAttribute(sinkhorn_fwd_small_kernel<EPT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)(160 * 1024)));
-      attr = true;
-    }
     const size_t tile_bytes = (size_t)(lpr_of(EPT) * EPT) * (lpr_of(EPT) * EPT + 4) * sizeof(float);   // load_slices_tile
     KCCOT_CUDA(launch_pdl(sinkhorn_fwd_small_kernel<EPT, true>, dim3(nsolve), dim3(threads),
                           hist_bytes > tile_bytes ? hist_bytes : tile_bytes, st, C, B, eps, L, Lmin,
@@ -949,12 +947,10 @@ static int launch_bwd_t(const float* C, int nsolve, int B, float eps, int L, con
                         cudaStream_t st, SinkhornMix mix) {
   const size_t hist_bytes = (size_t)2 * (L + 1) * lpr_of(EPT) * (EPT + 4) * sizeof(float);
   if (hist_bytes <= 160 * 1024) {
-    static size_t attr = 0;
-    if (hist_bytes > attr) {
+    static size_t attr[kMaxDevices] = {};
+    if (smem_attr_needed(attr, 160 * 1024))
       KCCOT_CUDA(cudaFuncSetAttribute(sinkhorn_bwd_small_kernel<EPT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)(160 * 1024)));
-      attr = 160 * 1024;
-    }
     const size_t tile_bytes = (size_t)(lpr_of(EPT) * EPT) * (lpr_of(EPT) * EPT + 1) * sizeof(float);      // Cbar transposition tile of the epilogue
     KCCOT_CUDA(launch_pdl(sinkhorn_bwd_small_kernel<EPT, true>, dim3(nsolve), dim3(threads),
                           hist_bytes > tile_bytes ? hist_bytes : tile_bytes, st, C, B, eps, L, u_hist, v_hist, nits, gcost,
