@@ -1,5 +1,7 @@
 // Internal interfaces of the cost path (shared by cost_simt.cu, gram_tcgen05.cu, cost_abi.cu).
 #pragma once
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace kccot {
@@ -71,5 +73,51 @@ int launch_grad_tc(const float* Cbar3, const float* x, const float* y, int nprob
                    float s, float* gx, float* gy, int accumulate, float* Wws, cudaStream_t st);
 int launch_grad_pair_tc(const float* Cbar, const float* x, const float* y, int nprob, int Bx, int By, long long K,
                         float s, float* gx, float* gy, int accumulate, float* Wws, cudaStream_t st);
+
+// ------------------------------------------------------------------------------------------------
+// Large-batch path (B > 64): gemm_f16x3.cu / large_prep.cu / large_abi.cu
+// ------------------------------------------------------------------------------------------------
+#define G3_BM 128
+#define G3_BN 256
+#define G3_BK 64
+struct G3Job {
+  int a_row0, b_row0;      // first row of this block in the A / B operand arrays
+  int m, n;                // valid rows / columns of the block
+  int tm, tn, ntiles;      // filled by g3_count_tiles
+  int tri;                 // symmetric block (a_row0 == b_row0): only tiles touching the upper triangle
+  float* out;              // [ksplit][m][ld]
+  long long ld, ks_stride;
+};
+struct G3Params {
+  G3Job job[3];
+  int njobs, ntiles_total;
+  int nkb, ksplit, kb_per_split;
+  int drain;               // k-blocks per accumulation chunk (see gemm_f16x3.cu)
+  float alpha;
+  const float* alpha_dev;  // optional device scalar multiplied into alpha
+  int accumulate;          // add into `out` instead of overwriting it
+};
+int g3_count_tiles(G3Job* jb);
+void g3_plan_split(int ntiles, int nkb, int* ksplit, int* kb_per_split);
+// A*: [a_rows][a_pitch] fp16 (hi, lo), B*: [b_rows][b_pitch]; contraction over `kdim` leading columns
+int launch_gemm_f16x3(const __half* A1, const __half* A2, long long a_rows, long long a_pitch_elems,
+                      const __half* B1, const __half* B2, long long b_rows, long long b_pitch_elems, long long kdim,
+                      G3Params P, cudaStream_t st);
+
+// large_abi.cu: true when the large-batch path takes the shape
+bool large_path_wanted(int Bx, int By, bool same);
+size_t large_cost_fwd_ws_bytes(int Bx, int By, long long K, bool same, bool mixed);
+size_t large_cost_bwd_ws_bytes(int Bx, int By, long long K, bool mixed);
+int large_mixed_cost_fwd(const float* real, const float* fake, int B, long long K, const float* h_fake,
+                         const float* m_real, const float* h_real, const float* m_fake, int T, int J, float s,
+                         float* C3, void* ws, size_t ws_bytes, cudaStream_t st);
+int large_mixed_cost_bwd(const float* Cbar3, const float* real, const float* fake, int B, long long K, float s,
+                         float* g_real, float* g_fake, int accumulate, void* ws, size_t ws_bytes, cudaStream_t st);
+int large_cost_fwd(const float* x, const float* y, int Bx, int By, long long K, const float* h1, const float* M1,
+                   const float* h2, const float* M2, int T, int J, float s, float* C, void* ws, size_t ws_bytes,
+                   cudaStream_t st);
+int large_cost_bwd(const float* Cbar, const float* x, const float* y, int Bx, int By, long long K, float s, float* gx,
+                   float* gy, int accumulate, void* ws, size_t ws_bytes, cudaStream_t st);
+void large_set_drain(int k_blocks);
 
 }  // namespace kccot

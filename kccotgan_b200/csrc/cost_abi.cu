@@ -40,7 +40,16 @@ extern "C" {
 size_t kccot_cost_workspace_bytes(int nprob, int Bx, int By, long long K) {
   if (nprob < 1 || Bx < 1 || By < 1 || K < 1) return 0;
   size_t a = simt_part_bytes(nprob, Bx, By, K);
-  if (Bx + By <= 128) a = a > tc_part_bytes(nprob, Bx + By, K) ? a : tc_part_bytes(nprob, Bx + By, K);
+  // the stacked-row tensor-core kernel takes [x; y] (rows Bx + By) or, for a self-cost (x == y), x alone (rows Bx):
+  // size for whichever the launcher may pick
+  if (Bx + By <= 128 || (Bx == By && Bx <= 128)) {
+    const size_t t = tc_part_bytes(nprob, Bx + By <= 128 ? Bx + By : Bx, K);
+    a = a > t ? a : t;
+  }
+  if (large_path_wanted(Bx, By, false)) {
+    const size_t l = large_cost_fwd_ws_bytes(Bx, By, K, false, false);
+    a = a > l ? a : l;
+  }
   return align_up(a, 256);
 }
 
@@ -55,6 +64,17 @@ int kccot_cost_fwd(const float* x, const float* y, int nprob, int Bx, int By, lo
   cudaStream_t st = (cudaStream_t)stream;
   const bool same = (x == y);
   KCCOT_CHECK_ARG(!same || Bx == By, "x == y requires Bx == By");
+  if ((flags & 3) != KCCOT_PATH_SIMT && large_path_wanted(Bx, By, same)) {
+    for (int p = 0; p < nprob; ++p) {
+      const long long hm = (long long)T * J;
+      if (int rc = large_cost_fwd(x + (long long)p * Bx * K, same ? x + (long long)p * Bx * K : y + (long long)p * By * K, Bx, By,
+                                  K, h1 ? h1 + p * Bx * hm : nullptr, M1 ? M1 + p * By * hm : nullptr,
+                                  h2 ? h2 + p * Bx * hm : nullptr, M2 ? M2 + p * By * hm : nullptr, T, J, s,
+                                  C + (long long)p * Bx * By, ws, ws_bytes, st))
+        return rc;
+    }
+    return KCCOT_OK;
+  }
   const bool tc_ok = same ? tc_sqdist_supported(x, nullptr, Bx, 0, K) : tc_sqdist_supported(x, y, Bx, By, K);
   const int path = pick_path(flags, tc_ok);
   if (path < 0) {
@@ -92,6 +112,10 @@ size_t kccot_mixed_cost_workspace_bytes(int nprob, int B, long long K) {
   if (nprob < 1 || B < 1 || K < 1) return 0;
   size_t a = 3 * align_up(simt_part_bytes(nprob, B, B, K), 256);
   if (2 * B <= 128) a = a > tc_part_bytes(nprob, 2 * B, K) ? a : tc_part_bytes(nprob, 2 * B, K);
+  if (large_path_wanted(B, B, false)) {
+    const size_t l = large_cost_fwd_ws_bytes(B, B, K, false, true);
+    a = a > l ? a : l;
+  }
   return align_up(a, 256);
 }
 
@@ -111,6 +135,16 @@ int mixed_cost_fwd_impl(const float* real, const float* fake, int nprob, int B, 
   KCCOT_CHECK_ARG(real && fake && h_fake && m_real && h_real && m_fake && C3 && ws, "null pointer");
   KCCOT_CHECK_ARG(T >= 2 && J >= 1, "martingale term needs T >= 2, J >= 1 (T=%d J=%d)", T, J);
   cudaStream_t st = (cudaStream_t)stream;
+  if ((flags & 3) != KCCOT_PATH_SIMT && real != fake && large_path_wanted(B, B, false)) {
+    const long long hm = (long long)B * T * J;
+    for (int p = 0; p < nprob; ++p)
+      if (int rc = large_mixed_cost_fwd(real + (long long)p * B * K, fake + (long long)p * B * K, B, K, h_fake + p * hm,
+                                        m_real + p * hm, h_real + p * hm, m_fake + p * hm, T, J, s,
+                                        C3 + (long long)p * 3 * B * B, ws, ws_bytes, st))
+        return rc;
+    if (zero_counters) KCCOT_CUDA(cudaMemsetAsync(zero_counters, 0, (size_t)nprob * sizeof(int), st));
+    return KCCOT_OK;
+  }
   const bool tc_ok = (real != fake) && tc_sqdist_supported(real, fake, B, B, K);
   const int path = pick_path(flags, tc_ok);
   if (path < 0) {
@@ -192,8 +226,9 @@ int kccot_mixed_sqdist_partials(const float* real, const float* fake, int nprob,
 }
 
 size_t kccot_cost_bwd_workspace_bytes(int nprob, int Bx, int By, long long K) {
-  (void)K;
-  return align_up((size_t)(nprob > 0 ? nprob : 1) * 128 * 128 * sizeof(float) * (Bx + By <= 128 ? 1 : 0) + 256, 256);
+  if (nprob < 1 || Bx < 1 || By < 1 || K < 1) return 0;
+  if (large_path_wanted(Bx, By, false)) return large_cost_bwd_ws_bytes(Bx, By, K, false);
+  return align_up((size_t)nprob * 128 * 128 * sizeof(float) * (Bx + By <= 128 ? 1 : 0) + 256, 256);
 }
 
 int kccot_cost_bwd(const float* Cbar, const float* x, const float* y, int nprob, int Bx, int By, long long K, float s,
@@ -203,6 +238,15 @@ int kccot_cost_bwd(const float* Cbar, const float* x, const float* y, int nprob,
   cudaStream_t st = (cudaStream_t)stream;
   const int acc = (flags & KCCOT_FLAG_ACCUMULATE) ? 1 : 0;
   const long long cprob = (long long)Bx * By;
+  if ((flags & 3) != KCCOT_PATH_SIMT && large_path_wanted(Bx, By, false) && ws &&
+      ws_bytes >= large_cost_bwd_ws_bytes(Bx, By, K, false)) {
+    for (int p = 0; p < nprob; ++p)
+      if (int rc = large_cost_bwd(Cbar + p * cprob, x + (long long)p * Bx * K, y + (long long)p * By * K, Bx, By, K, s,
+                                  gx ? gx + (long long)p * Bx * K : nullptr, gy ? gy + (long long)p * By * K : nullptr, acc, ws,
+                                  ws_bytes, st))
+        return rc;
+    return KCCOT_OK;
+  }
   const bool tc_ok = (flags & 3) != KCCOT_PATH_SIMT && x != y && gx != gy && ws &&
                      ws_bytes >= (size_t)nprob * 128 * 128 * 4 && tc_grad_supported(x, y, Bx, By, K, gx, gy);
   if ((flags & 3) == KCCOT_PATH_TCGEN05 && !tc_ok) {
@@ -228,8 +272,8 @@ int kccot_martingale_bwd(const float* Cbar, const float* h, const float* M, int 
 }
 
 size_t kccot_mixed_cost_bwd_workspace_bytes(int nprob, int B, long long K) {
-  (void)K;
-  if (nprob < 1 || B < 1) return 0;
+  if (nprob < 1 || B < 1 || K < 1) return 0;
+  if (large_path_wanted(B, B, false)) return large_cost_bwd_ws_bytes(B, B, K, true);
   return align_up((size_t)nprob * 128 * 128 * sizeof(float) * (2 * B <= 128 ? 1 : 0) + 256, 256);
 }
 
@@ -259,6 +303,15 @@ int kccot_mixed_cost_bwd(const float* Cbar3, const float* real, const float* fak
   jobs.j[1] = MartJob{gm_real, Cxy, h_fake, Cxx, h_real, cprob, Bi, Bi, Bi, 1, 1, acc};
   jobs.j[2] = MartJob{gh_real, Cxx, m_real, nullptr, nullptr, cprob, Bi, Bi, Bi, 0, 0, acc};
   jobs.j[3] = MartJob{gm_fake, Cyy, h_fake, nullptr, nullptr, cprob, Bi, Bi, Bi, 1, 1, acc};
+  if (want_tc && real != fake && large_path_wanted(B, B, false) && ws && ws_bytes >= large_cost_bwd_ws_bytes(B, B, K, true)) {
+    if (int rc = launch_martingale_jobs(jobs, 4, nprob, T, J, s, st)) return rc;
+    for (int p = 0; p < nprob; ++p)
+      if (int rc = large_mixed_cost_bwd(Cbar3 + p * cprob, real + (long long)p * B * K, fake + (long long)p * B * K, B, K, s,
+                                        g_real ? g_real + (long long)p * B * K : nullptr,
+                                        g_fake ? g_fake + (long long)p * B * K : nullptr, acc, ws, ws_bytes, st))
+        return rc;
+    return KCCOT_OK;
+  }
   if (tc_ok) {
     // The martingale adjoint (a few MFLOP, ~10 us of latency) and the gradient GEMM both depend on Cbar3
     // only: the small kernel goes first on the side stream and the persistent GEMM CTAs fill in around it.

@@ -305,6 +305,28 @@ int encode_tmap_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1,
   return KCCOT_OK;
 }
 
+int encode_tmap_2d_f16(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows, uint64_t pitch_bytes,
+                       uint32_t box_cols, uint32_t box_rows) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return KCCOT_ECUDA;
+  }
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {pitch_bytes};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (fp16 2-D) failed with CUresult %d (dims %llu x %llu, pitch %llu, box %u x %u)", (int)r,
+              (unsigned long long)cols, (unsigned long long)rows, (unsigned long long)pitch_bytes, box_cols, box_rows);
+    return KCCOT_ECUDA;
+  }
+  return KCCOT_OK;
+}
+
 bool tc_sqdist_supported(const float* x, const float* y, int Bx, int By, long long K) {
   const int R = Bx + (y ? By : 0);
   if (R > kRows || Bx % 8 != 0 || (y && By % 8 != 0)) return false;

@@ -257,6 +257,10 @@ __global__ void __launch_bounds__(lpr_of(EPT) * lpr_of(EPT) * EPT) sinkhorn_fwd_
   __shared__ __align__(16) float as[BMP], bs[BMP];      // linear scalings a_i, b_j of the fast path (padded)
   __shared__ float red[32];
   __shared__ int stop_flag, bad_flag;
+  // range-guard flags of the post-`first_check` loop, one per iteration parity: iteration `it` writes bad2[it & 1]
+  // and iteration it + 1 reads it, so a read and the next write of the same word are always two barriers apart
+  // (a single flag let a fast warp's write of iteration it race with a slow warp's read at the top of it)
+  __shared__ int bad2[2];
   const int n = blockIdx.x;
   const int tid = threadIdx.x, i = tid / LPR, q = tid % LPR;
   const int ic = min(i, BM - 1);
@@ -297,7 +301,7 @@ __global__ void __launch_bounds__(lpr_of(EPT) * lpr_of(EPT) * EPT) sinkhorn_fwd_
   for (int t = tid; t < BM; t += blockDim.x) { urow(0)[t] = 0.f; vrow(0)[t] = 0.f; }
   for (int t = tid; t < BMP; t += blockDim.x) { as[t] = 0.f; bs[t] = 0.f; }
   if (!HS && tid < B) { uh[tid] = 0.f; vh[tid] = 0.f; }
-  if (tid == 0) { stop_flag = 0; bad_flag = 0; }
+  if (tid == 0) { stop_flag = 0; bad_flag = 0; bad2[0] = 0; bad2[1] = 0; }
   __syncthreads();
   if (owner) { as[ip] = alpha; bs[ip] = 1.f; }   // stage the row minima for the column slices; b = exp2(0)
   __syncthreads();
@@ -405,7 +409,7 @@ __global__ void __launch_bounds__(lpr_of(EPT) * lpr_of(EPT) * EPT) sinkhorn_fwd_
       if (!slow) {
         // ---- fast u update: s_i = sum_j Kt_ij b_j (straight-line; only the stores are predicated)
         const float s = dot_slice<EPT>(Kr, bs_q);
-        if (bad_flag) {
+        if (bad2[(it + 1) & 1]) {
           // a scaling left the safe range during iteration it-1: roll back to the potentials before
           // it (history row it-1) and redo it in the log domain
           slow = true;
@@ -424,7 +428,7 @@ __global__ void __launch_bounds__(lpr_of(EPT) * lpr_of(EPT) * EPT) sinkhorn_fwd_
           as[ip] = a;
           urow(it + 1)[i] = unew;
           if (!HS) uh[(long long)(it + 1) * B + i] = unew;
-          if (!(s > kLo && s < kHi)) bad_flag = 1;
+          if (!(s > kLo && s < kHi)) bad2[it & 1] = 1;
         }
         __syncthreads();
         // ---- fast v update: t_j = sum_i Kt_ij a_i -------------------------------------------
@@ -435,7 +439,7 @@ __global__ void __launch_bounds__(lpr_of(EPT) * lpr_of(EPT) * EPT) sinkhorn_fwd_
           bs[ip] = bnew;
           vrow(it + 1)[i] = vnew;
           if (!HS) vh[(long long)(it + 1) * B + i] = vnew;
-          if (!(t > kLo && t < kHi)) bad_flag = 1;
+          if (!(t > kLo && t < kHi)) bad2[it & 1] = 1;
         }
         __syncthreads();
       } else {
@@ -459,7 +463,7 @@ __global__ void __launch_bounds__(lpr_of(EPT) * lpr_of(EPT) * EPT) sinkhorn_fwd_
       // ---- stopping rule (gan_utils.py:157-160 / :114-117); can only fire once the minimum count
       // is reached, so the reduction is skipped before that -------------------------------------
       const bool may_stop = exit_on_index ? (it >= Lmin) : (nits >= Lmin);
-      if (may_stop && nits < L && (slow || !bad_flag)) {
+      if (may_stop && nits < L && (slow || !bad2[it & 1])) {
         const float err = block_reduce(owner ? du : 0.f, red, false) / kscale;
         if (tid == 0) stop_flag = (thresh > err) ? 1 : 0;
         __syncthreads();
@@ -468,7 +472,7 @@ __global__ void __launch_bounds__(lpr_of(EPT) * lpr_of(EPT) * EPT) sinkhorn_fwd_
       ++it;
     }
     // the last executed iteration may itself have tripped the guard
-    if (!slow && bad_flag && nits > 0) {
+    if (!slow && nits > 0 && bad2[(nits - 1) & 1]) {
       slow = true;
       it = nits - 1;
       __syncthreads();

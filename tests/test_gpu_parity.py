@@ -330,6 +330,32 @@ def test_sinkhorn_guard_path(B, eps, L):
         assert e < 2e-3          # eps this small makes the plan a near-permutation: ill-conditioned gradient
 
 
+@pytest.mark.parametrize("B,na,nb,D", [(32, 20, 12, 150.0), (64, 40, 24, 200.0)])
+def test_sinkhorn_guard_trips_late(B, na, nb, D):
+    """Two unbalanced clusters behind a cost barrier: the potentials drift by ~0.5 per iteration and the scaling
+    form leaves its fp32 range only around iteration 115 — after the tight loop (Lmin = 100 < L = 150), in the
+    loop whose roll-back used to be decided through an unsynchronised flag (sinkhorn_small.cu)."""
+    from kccotgan_b200.functional import SinkhornFn
+    from oracle import closed_form as cf
+    rng = np.random.default_rng(0)
+    C = np.full((B, B), D)
+    C[:na, :nb] = 0.0
+    C[na:, nb:] = 0.0
+    C = (C + rng.random((B, B))).astype(np.float32)
+    L = 150
+    for rep in range(3):                                  # a race shows up as a hang or as run-to-run differences
+        Ct = torch.from_numpy(C[None]).cuda().requires_grad_(True)
+        cost, nits = SinkhornFn.apply(Ct, 1.0, L, 100, 1e-2, False)
+        gC, = torch.autograd.grad(cost.sum(), Ct)
+        ref, uh, vh, rn = cf.sinkhorn_forward(C.astype(np.float64), 1.0, L, Lmin=100, thresh=1e-2)
+        Cb = cf.sinkhorn_backward(C.astype(np.float64), 1.0, uh, vh, rn)
+        e = rel_l2(gC[0].cpu().numpy(), Cb)
+        print("late guard", B, "nits", int(nits[0]), rn, "cost", float(cost[0]), ref, "Cbar", e)
+        assert int(nits[0]) == rn
+        assert abs(float(cost[0]) - ref) <= LOSS_TOL * max(abs(ref), 1.0)
+        assert e < 2e-3
+
+
 # ---------------------------------------------------------------------------------------------
 # smoothing
 # ---------------------------------------------------------------------------------------------
