@@ -41,4 +41,22 @@ int stream_sinkhorn_fwd(const float* C, int B, float eps, int L, int Lmin, float
 int stream_sinkhorn_bwd(const float* C, int B, float eps, int L, const float* u_hist, const float* v_hist,
                         const int32_t* nits, const float* gcost, float* Cbar, void* ws, cudaStream_t st);
 
+// sinkhorn_persist.cu — all iterations inside one cooperative kernel (64 < B <= 8192, B % 4 == 0); row shards
+// exchange their column sums inside the kernel through peer-mapped mailboxes.
+constexpr int kMaxShardRanks = 8;
+struct ShardComm {
+  int nranks, rank;
+  float* mbox[kMaxShardRanks];        // mailbox of every rank (device pointers valid on THIS device)
+  unsigned* flags[kMaxShardRanks];    // epoch flags of every rank, [nranks] each
+};
+bool persist_supported(int Brows, int B, int L);
+size_t persist_workspace_bytes(int np, int Brows, int B, int L);
+size_t persist_mailbox_floats(int np, int nranks, int B);
+int persist_sinkhorn_fwd(const float* C, int np, int Brows, int B, int row0, float eps, int L, int Lmin, float thresh,
+                         int exit_on_index, float* u_hist, float* v_hist, int32_t* nits, float* cost, void* ws,
+                         const ShardComm* comm, const float* shift_dev, cudaStream_t st);
+int persist_sinkhorn_bwd(const float* C, int np, int Brows, int B, int row0, float eps, int L, const float* u_hist,
+                         const float* v_hist, const int32_t* nits, const float* gcost, float gcost_host, float* Cbar,
+                         void* ws, const ShardComm* comm, const float* shift_dev, cudaStream_t st);
+
 }  // namespace kccot
