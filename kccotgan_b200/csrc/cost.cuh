@@ -66,7 +66,9 @@ int launch_sqdist_partials_tc(const float* x, const float* y, int nprob, int Bx,
 
 // grad_tcgen05.cu — tensor-core adjoint over the stacked rows z = [x; y] (see the file header).
 // Wws: [nprob, R, R] fp32 scratch for the weight matrix.  gx / gy may be null.
+#ifdef KCCOT_DEV
 void set_grad_trace(long long* b);
+#endif
 bool tc_grad_supported(const float* x, const float* y, int Bx, int By, long long K, const float* gx,
                        const float* gy);
 int launch_grad_tc(const float* Cbar3, const float* x, const float* y, int nprob, int Bx, int By, long long K,
@@ -98,7 +100,12 @@ struct G3Params {
   int accumulate;          // add into `out` instead of overwriting it
 };
 int g3_count_tiles(G3Job* jb);
-void g3_plan_split(int ntiles, int nkb, int* ksplit, int* kb_per_split);
+int g3_count_tiles_pair(G3Job* jb);     // 256 x 256 tiles of the CTA-pair kernel (gemm_f16x3_2cta.cu)
+// `units`: CTAs (single-CTA kernel) or clusters (pair kernel) to fill
+void g3_plan_split(int ntiles, int nkb, int units, int* ksplit, int* kb_per_split);
+int launch_gemm_f16x3_pair(const __half* A1, const __half* A2, long long a_rows, long long a_pitch_elems,
+                           const __half* B1, const __half* B2, long long b_rows, long long b_pitch_elems, long long kdim,
+                           G3Params P, cudaStream_t st);
 // A*: [a_rows][a_pitch] fp16 (hi, lo), B*: [b_rows][b_pitch]; contraction over `kdim` leading columns
 int launch_gemm_f16x3(const __half* A1, const __half* A2, long long a_rows, long long a_pitch_elems,
                       const __half* B1, const __half* B2, long long b_rows, long long b_pitch_elems, long long kdim,
@@ -119,5 +126,6 @@ int large_cost_fwd(const float* x, const float* y, int Bx, int By, long long K, 
 int large_cost_bwd(const float* Cbar, const float* x, const float* y, int Bx, int By, long long K, float s, float* gx,
                    float* gy, int accumulate, void* ws, size_t ws_bytes, cudaStream_t st);
 void large_set_drain(int k_blocks);
+void large_set_pair(int use_pair);
 
 }  // namespace kccot

@@ -1,5 +1,6 @@
 // Development probes (not part of the product path): raw TMA streaming throughput for the box
 // shapes the cost kernels use.  Exposed as kccot_debug_* so that scripts/ can time them on a B200.
+#ifdef KCCOT_DEV      // compiled only into the development library (python -m kccotgan_b200.build --dev -> libkccot_dev.so)
 #include "cost.cuh"
 #include "tc_common.cuh"
 
@@ -171,3 +172,10 @@ extern "C" int kccot_debug_matvec_probe(int lpr, int iters, const float* C, long
   else matvec_probe_kernel<4><<<3, 256, 0, st>>>(C, iters, cycles, ab_out);
   return (int)cudaGetLastError();
 }
+
+// large-batch GEMM knobs: drain period in k-blocks (0 = kernel default), CTA-pair kernel on/off
+extern "C" void kccot_debug_large_config(int drain_k_blocks, int use_pair) {
+  kccot::large_set_drain(drain_k_blocks);
+  kccot::large_set_pair(use_pair);
+}
+#endif  // KCCOT_DEV

@@ -268,8 +268,8 @@ int g3_count_tiles(G3Job* jb) {
 }
 
 // k-split so that the grid is filled when the tile count is small (mid-size B); each split keeps >= 8 k-blocks
-void g3_plan_split(int ntiles, int nkb, int* ksplit, int* kb_per_split) {
-  const int sms = num_sms();
+void g3_plan_split(int ntiles, int nkb, int units, int* ksplit, int* kb_per_split) {
+  const int sms = units;
   int ks = 1;
   if (ntiles < sms) {
     ks = (sms + ntiles - 1) / ntiles;

@@ -111,9 +111,14 @@ grad_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ 
   Bars& bars = *reinterpret_cast<Bars*>(obuf + 2 * kObufBytes);
 
   const int p = blockIdx.y;
+#ifdef KCCOT_DEV
   const bool tr = (trace != nullptr) && blockIdx.x == 1 && blockIdx.y == 0;   // development timeline of one CTA
-  int trn = 0;
 #define KTRACE(role, ev) do { if (tr && trn < 64) trace[((role) * 64 + trn) * 2 + (ev)] = clock64(); } while (0)
+#else
+  (void)trace;                  // the timeline exists only in the development build (python -m kccotgan_b200.build --dev)
+#define KTRACE(role, ev) do { } while (0)
+#endif
+  int trn = 0;
   const long long ntiles = (K + kCols - 1) / kCols;
   // each CTA streams a CONTIGUOUS range of column tiles: consecutive 128-byte segments of a row are
   // fetched by the same SM back to back (DRAM page / L2 256-byte promotion locality)
@@ -410,7 +415,11 @@ grad_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ 
   if (warp == 1) tc::tmem_dealloc(tmem, kTmemCols);
 }
 
-static long long* g_grad_trace = nullptr;     // development only: set through kccot_debug_set_grad_trace
+#ifdef KCCOT_DEV
+static long long* g_grad_trace = nullptr;     // set through kccot_debug_set_grad_trace (development build only)
+#else
+static constexpr long long* g_grad_trace = nullptr;
+#endif
 struct GradPlan { int nstages; size_t smem; };
 GradPlan plan_grad(int Bx, int By, int N) {
   (void)N;
@@ -426,7 +435,9 @@ GradPlan plan_grad(int Bx, int By, int N) {
 }
 }  // namespace
 
+#ifdef KCCOT_DEV
 void set_grad_trace(long long* b) { g_grad_trace = b; }
+#endif
 
 bool tc_grad_supported(const float* x, const float* y, int Bx, int By, long long K, const float* gx, const float* gy) {
   if (Bx % 8 || By % 8 || Bx + By > 128 || Bx > kMaxN || By > kMaxN || Bx < 8 || By < 8) return false;
@@ -504,5 +515,7 @@ int launch_grad_pair_tc(const float* Cbar, const float* x, const float* y, int n
 
 }  // namespace kccot
 
-// development only: device buffer of 4 roles x 64 records x 2 timestamps (clock64) filled by CTA 1
+#ifdef KCCOT_DEV
+// development build only: device buffer of 4 roles x 64 records x 2 timestamps (clock64) filled by CTA 1
 extern "C" void kccot_debug_set_grad_trace(long long* buf) { kccot::set_grad_trace(buf); }
+#endif

@@ -7,7 +7,8 @@
 namespace kccot {
 
 namespace {
-int g_drain = 16;       // k-blocks per accumulation chunk of the GEMM (development knob, kccot_debug_* only)
+int g_drain = 0;        // k-blocks per accumulation chunk of the GEMM; 0 = the kernel's default (development knob)
+bool g_pair = true;     // CTA-pair kernel (gemm_f16x3_2cta.cu); false: single-CTA 128 x 256 tiles (development knob)
 
 struct Carver {
   char* base;
@@ -60,8 +61,8 @@ FwdWs carve_fwd(void* ws, int Bx, int By, long long K, bool same, bool mixed) {
     w.job[0] = G3Job{0, Bx, Bx, By, 0, 0, 0, 0, nullptr, By, 0};
   }
   int ntiles = 0;
-  for (int j = 0; j < w.njobs; ++j) ntiles += g3_count_tiles(&w.job[j]);
-  g3_plan_split(ntiles, (int)(w.Kp / G3_BK), &w.ksplit, &w.kb_per_split);
+  for (int j = 0; j < w.njobs; ++j) ntiles += g_pair ? g3_count_tiles_pair(&w.job[j]) : g3_count_tiles(&w.job[j]);
+  g3_plan_split(ntiles, (int)(w.Kp / G3_BK), g_pair ? num_sms() / 2 : num_sms(), &w.ksplit, &w.kb_per_split);
   Carver c(ws);
   w.scal = c.take<float>(kScalCount);
   w.part = c.take<float>((size_t)w.nseg * K);
@@ -123,6 +124,7 @@ int run_fwd(const FwdWs& w, const float* x, const float* y, int Bx, int By, long
   P.drain = g_drain;
   P.alpha = 1.f;
   P.alpha_dev = nullptr;
+  if (g_pair) return launch_gemm_f16x3_pair(w.Zh1, w.Zh2, R, w.Kp, w.Zh1, w.Zh2, R, w.Kp, K, P, st);
   return launch_gemm_f16x3(w.Zh1, w.Zh2, R, w.Kp, w.Zh1, w.Zh2, R, w.Kp, K, P, st);
 }
 
@@ -134,7 +136,8 @@ int run_bwd_rows(const BwdWs& w, const float* Cxx, const float* Cxy, const float
     return rc;
   G3Params P{};
   P.job[0] = G3Job{0, 0, nrows, (int)K, 0, 0, 0, 0, g, K, 0};
-  g3_count_tiles(&P.job[0]);
+  if (g_pair) g3_count_tiles_pair(&P.job[0]);
+  else g3_count_tiles(&P.job[0]);
   P.njobs = 1;
   P.ksplit = 1;
   P.kb_per_split = (int)(w.Rp / G3_BK);
@@ -142,11 +145,13 @@ int run_bwd_rows(const BwdWs& w, const float* Cxx, const float* Cxy, const float
   P.alpha = -2.f * s;
   P.alpha_dev = w.scal + kScalGradAlpha;
   P.accumulate = accumulate;
+  if (g_pair) return launch_gemm_f16x3_pair(w.Wh1, w.Wh2, nrows, w.Rp, w.ZT1, w.ZT2, K, w.Rp, R, P, st);
   return launch_gemm_f16x3(w.Wh1, w.Wh2, nrows, w.Rp, w.ZT1, w.ZT2, K, w.Rp, R, P, st);
 }
 }  // namespace
 
-void large_set_drain(int k_blocks) { g_drain = k_blocks > 0 ? k_blocks : 16; }
+void large_set_drain(int k_blocks) { g_drain = k_blocks > 0 ? k_blocks : 0; }
+void large_set_pair(int use_pair) { g_pair = use_pair != 0; }
 
 bool large_path_wanted(int Bx, int By, bool same) { return (same ? Bx : Bx + By) > 128; }
 

@@ -907,10 +907,15 @@ __global__ void __launch_bounds__(lpr_of(EPT) * lpr_of(EPT) * EPT) sinkhorn_bwd_
   SK_STAMP(1, 7);
 }
 
-// forward, 32 < B <= 64: two lanes per row by default; KCCOT_SK_LANES=4 selects the four-lane mapping (A/B timing)
+// forward, 32 < B <= 64: two lanes per row; the development build (KCCOT_DEV) can select the four-lane mapping
+// with KCCOT_SK_LANES=4 for A/B timing
 static bool four_lanes() {
+#ifdef KCCOT_DEV
   static const bool v = [] { const char* e = getenv("KCCOT_SK_LANES"); return e && atoi(e) == 4; }();
   return v;
+#else
+  return false;
+#endif
 }
 
 template <int EPT>
