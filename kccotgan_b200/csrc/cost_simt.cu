@@ -501,12 +501,100 @@ __global__ void __launch_bounds__(256) martingale_bwd_kernel(MartJobs jobs, int 
   }
 }
 
+// Large batches (B >= 256): the same products as a tiled GEMM.  One CTA = one job, TR = 64 output rows, all
+// T*J <= 256 columns; the contraction is staged in chunks of 32 (weights [64 x 32], raw rows of X [32 x T*J]);
+// thread (ty, tx) owns rows 8 ty .. 8 ty + 7 and columns tx + 32 c.  martingale_bwd_kernel re-reads all of X for
+// every 4 output rows (25 ms at B = 8192); this one reads it once per 64 rows.
+constexpr int TR = 64, TKC = 32;
+__global__ void __launch_bounds__(256) martingale_bwd_tiled_kernel(MartJobs jobs, int T, int J, float s) {
+  extern __shared__ float4 sh4[];
+  float* sh = reinterpret_cast<float*>(sh4);
+  const MartJob& jb = jobs.j[blockIdx.y];
+  const int r0 = blockIdx.x * TR, p = blockIdx.z;
+  if (r0 >= jb.nrows || jb.out == nullptr) return;
+  const int TJ = T * J;
+  float* Xs = sh;                          // [TKC][TJ]
+  float* Ws = sh + TKC * TJ;               // [TR][TKC + 1]
+  const int t = threadIdx.x, tx = t & 31, ty = t >> 5;
+  float acc[8][8];
+#pragma unroll
+  for (int a = 0; a < 8; ++a)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[a][c] = 0.f;
+  for (int src = 0; src < 2; ++src) {
+    const float* C = src ? jb.C2 : jb.C1;
+    if (C == nullptr) continue;
+    C += (long long)p * jb.cprob;
+    const float* X = (src ? jb.X2 : jb.X1) + (long long)p * jb.ncontr * TJ;
+    for (int k0 = 0; k0 < jb.ncontr; k0 += TKC) {
+      const int kc = min(TKC, jb.ncontr - k0);
+      __syncthreads();
+      for (int e = t; e < TKC * TJ; e += 256) Xs[e] = (e < kc * TJ) ? X[(long long)k0 * TJ + e] : 0.f;
+      if (!jb.transposed) {
+        for (int e = t; e < TR * TKC; e += 256) {
+          const int rr = e / TKC, k = e % TKC;
+          Ws[rr * (TKC + 1) + k] = (r0 + rr < jb.nrows && k < kc) ? C[(long long)(r0 + rr) * jb.ld + k0 + k] : 0.f;
+        }
+      } else {
+        for (int e = t; e < TR * TKC; e += 256) {
+          const int k = e / TR, rr = e % TR;
+          Ws[rr * (TKC + 1) + k] = (r0 + rr < jb.nrows && k < kc) ? C[(long long)(k0 + k) * jb.ld + r0 + rr] : 0.f;
+        }
+      }
+      __syncthreads();
+#pragma unroll 4
+      for (int k = 0; k < TKC; ++k) {
+        float w[8], x[8];
+#pragma unroll
+        for (int a = 0; a < 8; ++a) w[a] = Ws[(ty * 8 + a) * (TKC + 1) + k];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) x[c] = (tx + 32 * c < TJ) ? Xs[k * TJ + tx + 32 * c] : 0.f;
+#pragma unroll
+        for (int a = 0; a < 8; ++a)
+#pragma unroll
+          for (int c = 0; c < 8; ++c) acc[a][c] = fmaf(w[a], x[c], acc[a][c]);
+      }
+    }
+  }
+  // G -> shared memory [TR][TJ], then the (masked) time differences
+  __syncthreads();
+#pragma unroll
+  for (int a = 0; a < 8; ++a)
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      if (tx + 32 * c < TJ) sh[(ty * 8 + a) * TJ + tx + 32 * c] = acc[a][c];
+  __syncthreads();
+  for (int e = t; e < TR * TJ; e += 256) {
+    const int rr = e / TJ, q = e - rr * TJ;
+    const int r = r0 + rr;
+    if (r >= jb.nrows) continue;
+    const int tt = q / J;
+    const float* g = sh + rr * TJ;
+    float v;
+    if (jb.mode == 0) v = (tt < T - 1) ? g[q + J] - g[q] : 0.f;
+    else v = ((tt >= 1) ? g[q - J] : 0.f) - ((tt <= T - 2) ? g[q] : 0.f);
+    v *= s;
+    float* dst = jb.out + ((long long)p * jb.nrows + r) * TJ + q;
+    *dst = jb.acc ? *dst + v : v;
+  }
+}
+
 int launch_martingale_jobs(const MartJobs& jobs, int njobs, int nprob, int T, int J, float s, cudaStream_t st) {
   int maxrows = 0;
   for (int i = 0; i < njobs; ++i)
     if (jobs.j[i].out) maxrows = max(maxrows, jobs.j[i].nrows);
   if (maxrows == 0) return KCCOT_OK;
   const int TJ = T * J;
+  if (maxrows >= 256 && TJ <= 256) {
+    const size_t a = (size_t)(TKC * TJ + TR * (TKC + 1)) * sizeof(float), b = (size_t)TR * TJ * sizeof(float);
+    const size_t smem_t = a > b ? a : b;
+    static size_t attr_t[kMaxDevices] = {};
+    if (smem_t > 48 * 1024 && smem_attr_needed(attr_t, smem_t))
+      KCCOT_CUDA(cudaFuncSetAttribute(martingale_bwd_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
+    martingale_bwd_tiled_kernel<<<dim3((maxrows + TR - 1) / TR, njobs, nprob), 256, smem_t, st>>>(jobs, T, J, s);
+    KCCOT_LAUNCH_CHECK();
+    return KCCOT_OK;
+  }
   const size_t smem = (size_t)(2 * MKC * TJ + 2 * MR * MKC) * sizeof(float);
   if (MR * TJ > 8 * 256 || smem > 200 * 1024) {
     set_error("martingale adjoint: T*J = %d too large (max %d)", TJ, 8 * 256 / MR);

@@ -188,7 +188,12 @@ constexpr int FQ = 32;     // martingale contraction chunk
 
 __global__ void __launch_bounds__(256) large_finalize_kernel(LargeFin F, int T, int J, float s,
                                                              const float* __restrict__ scal) {
-  __shared__ float hs[64][FQ + 1], ms[64][FQ + 1];
+  // one buffer, two uses: the martingale operand tiles (2 x 64 x (FQ+1) floats), then the transposed source
+  // tile of a mirrored block (64 x 65 doubles)
+  __shared__ double sbuf[64 * 65];
+  float (*hs)[FQ + 1] = reinterpret_cast<float (*)[FQ + 1]>(sbuf);
+  float (*ms)[FQ + 1] = hs + 64;
+  double (*pt)[65] = reinterpret_cast<double (*)[65]>(sbuf);
   const LargeFinBlock& b = F.b[blockIdx.z];
   const int i0 = blockIdx.y * 64, j0 = blockIdx.x * 64;
   if (i0 >= b.Bx || j0 >= b.By) return;
@@ -232,6 +237,22 @@ __global__ void __launch_bounds__(256) large_finalize_kernel(LargeFin F, int T, 
       }
     }
   }
+  // Symmetric blocks hold only the 256 x 256 tiles on or above the diagonal (uniform over this 64 x 64 tile):
+  // the rest is the mirror image, read along ITS rows (coalesced) and transposed through shared memory.
+  const bool stored = !b.tri || ((j0 / G3_BN) >= (i0 / G3_BN));
+  if (!stored) {
+    __syncthreads();                                     // hs / ms are dead
+    for (int e = t; e < 64 * 64; e += 256) {
+      const int jj = e >> 6, ii = e & 63;                // source row j0 + jj, source column i0 + ii
+      double d = 0.0;
+      if (j0 + jj < b.By && i0 + ii < b.Bx) {
+        const float* pp = b.P + (long long)(j0 + jj) * b.ld + i0 + ii;
+        for (int ks = 0; ks < b.nks; ++ks) d += (double)pp[(long long)ks * b.ks_stride];
+      }
+      pt[jj][ii] = d;
+    }
+    __syncthreads();
+  }
 #pragma unroll
   for (int a = 0; a < 4; ++a) {
     const int i = i0 + ty * 4 + a;
@@ -245,11 +266,13 @@ __global__ void __launch_bounds__(256) large_finalize_kernel(LargeFin F, int T, 
       if (b.zero_diag && i == j) {
         out = s * mart[a][c];
       } else {
-        // symmetric blocks hold only the tiles with (j / 256) >= (i / 128) / 2; the rest is the mirror image
-        const bool stored = !b.tri || ((j / G3_BN) >= ((i / G3_BM) >> 1));
-        const float* pp = b.P + (stored ? (long long)i * b.ld + j : (long long)j * b.ld + i);
         double d = 0.0;
-        for (int ks = 0; ks < b.nks; ++ks) d += (double)pp[(long long)ks * b.ks_stride];
+        if (stored) {
+          const float* pp = b.P + (long long)i * b.ld + j;
+          for (int ks = 0; ks < b.nks; ++ks) d += (double)pp[(long long)ks * b.ks_stride];
+        } else {
+          d = pt[tx * 4 + c][ty * 4 + a];
+        }
         const double D = ((double)ni + (double)b.nj[j] - 2.0 * d) * (double)zinv * (double)zinv;
         out = s * (float)D + s * mart[a][c];
       }

@@ -178,11 +178,12 @@ class SinkhornFn(torch.autograd.Function):
 _SIZES = {}
 
 
-def _mixed_sizes(B, K, L):
-    key = (B, K, L)
+def _mixed_sizes(B, K, L, nprob=1):
+    key = (B, K, L, nprob)
     if key not in _SIZES:
         lib = _lib.load()
-        _SIZES[key] = (int(lib.kccot_mixed_loss_saved_bytes(1, B, L)), int(lib.kccot_mixed_loss_workspace_bytes(1, B, K, L)))
+        _SIZES[key] = (int(lib.kccot_mixed_loss_saved_bytes(nprob, B, L)),
+                       int(lib.kccot_mixed_loss_workspace_bytes(nprob, B, K, L)))
     return _SIZES[key]
 
 
@@ -255,6 +256,69 @@ class MixedLossFn(torch.autograd.Function):
 # ------------------------------------------------------------------------------------------------
 # martingale penalty
 # ------------------------------------------------------------------------------------------------
+class MixedLossBatchedFn(torch.autograd.Function):
+    """`nprob` independent problems in one C-ABI call per direction (BASELINE config 4): every tensor carries a
+    leading problem axis, the result is one loss per problem."""
+
+    @staticmethod
+    def forward(ctx, real, fake, h_fake, m_real, h_real, m_fake, s, eps, L):
+        real, fake = _check(real, "f_real"), _check(fake, "f_fake")
+        if real.dim() < 3 or real.shape != fake.shape:
+            raise ValueError(f"f_real / f_fake: expected equal shapes [nprob, B, ...], got {tuple(real.shape)} vs "
+                             f"{tuple(fake.shape)}")
+        P, B = real.shape[0], real.shape[1]
+        R, F = real.reshape(P, B, -1), fake.reshape(P, B, -1)
+        K = R.shape[2]
+        hs = [_check(t, n, 4) for t, n in ((h_fake, "h_fake"), (m_real, "m_real"), (h_real, "h_real"),
+                                           (m_fake, "m_fake"))]
+        T, J = hs[0].shape[2], hs[0].shape[3]
+        for t, n in zip(hs, ("h_fake", "m_real", "h_real", "m_fake")):
+            if tuple(t.shape) != (P, B, T, J):
+                raise ValueError(f"{n}: expected shape {(P, B, T, J)}, got {tuple(t.shape)}")
+        if T < 2:
+            raise ValueError(f"the martingale term needs at least 2 time steps, got T={T}")
+        dev = R.device
+        L = int(L)
+        saved_bytes, ws_bytes = _mixed_sizes(B, K, L, P)
+        saved = torch.empty(saved_bytes, dtype=torch.uint8, device=dev)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        loss = torch.empty(P, dtype=torch.float32, device=dev)
+        terms = torch.empty((P, 3), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.call("kccot_mixed_loss_fwd", _ptr(R), _ptr(F), P, B, K, _ptr(hs[0]), _ptr(hs[1]), _ptr(hs[2]),
+                      _ptr(hs[3]), T, J, float(s), float(eps), L, _ptr(saved), _ptr(loss), _ptr(terms), _ptr(ws),
+                      ws_bytes, _PATH["flags"], _stream(dev))
+        ctx.save_for_backward(R, F, *hs, saved)
+        ctx.meta = (real.shape, fake.shape, float(s), float(eps), L)
+        ctx.mark_non_differentiable(terms)
+        ctx.set_materialize_grads(False)
+        return loss, terms
+
+    @staticmethod
+    def backward(ctx, gloss, _gterms):
+        R, F, h_fake, m_real, h_real, m_fake, saved = ctx.saved_tensors
+        rshape, fshape, s, eps, L = ctx.meta
+        P, B, K = R.shape
+        T, J = h_fake.shape[2], h_fake.shape[3]
+        dev = R.device
+        need = ctx.needs_input_grad
+        if gloss is None:
+            return (None,) * 9
+        gloss = gloss.reshape(P).float().contiguous()
+        outs = [torch.empty_like(t) if need[i] else None for i, t in enumerate((R, F, h_fake, m_real, h_real, m_fake))]
+        _, ws_bytes = _mixed_sizes(B, K, L, P)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            _lib.call("kccot_mixed_loss_bwd", _ptr(gloss), _ptr(R), _ptr(F), P, B, K, _ptr(h_fake), _ptr(m_real),
+                      _ptr(h_real), _ptr(m_fake), T, J, s, eps, L, _ptr(saved), *[_ptr(o) for o in outs], _ptr(ws),
+                      ws_bytes, _PATH["flags"], _stream(dev))
+        if outs[0] is not None:
+            outs[0] = outs[0].reshape(rshape)
+        if outs[1] is not None:
+            outs[1] = outs[1].reshape(fshape)
+        return (*outs, None, None, None)
+
+
 class MartingalePenaltyFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, M, reg_lam, s):

@@ -14,7 +14,7 @@ Reference quirks are reproduced on purpose:
 """
 import torch
 
-from .functional import CostFn, MartingalePenaltyFn, MixedLossFn, SinkhornFn, _check
+from .functional import CostFn, MartingalePenaltyFn, MixedLossBatchedFn, MixedLossFn, SinkhornFn, _check
 
 __all__ = ["cost_xy", "modified_cost", "bi_causal_modified_cost", "benchmark_sinkhorn", "compute_sinkhorn",
            "compute_N", "scale_invariante_martingale_regularization", "compute_sinkhorn_loss"]
@@ -93,3 +93,12 @@ def sinkhorn_loss_terms(f_real, f_fake, scaling_coef, h_fake, m_real, h_real, m_
     """Not in the reference: the same fused solve, returning (loss, [loss_xy, loss_xx, loss_yy]) and
     honouring epsilon / L (what the reference's CLI flags were meant to control)."""
     return MixedLossFn.apply(f_real, f_fake, h_fake, m_real, h_real, m_fake, scaling_coef, epsilon, L)
+
+
+def compute_sinkhorn_loss_batched(f_real, f_fake, scaling_coef, h_fake, m_real, h_real, m_fake, epsilon=1.0, L=100):
+    """Not in the reference: `nprob` independent (real, fake, h, m) tuples in one call (BASELINE config 4:
+    "batched independent Sinkhorn problems").  Every tensor carries a leading problem axis
+    (f_* [nprob,B,...], h/m [nprob,B,T,J]); returns the [nprob] mixed losses of gan_utils.py:204-227, each
+    differentiable w.r.t. its own inputs.  Problems share nothing, so ranks can split them with no collective."""
+    loss, _ = MixedLossBatchedFn.apply(f_real, f_fake, h_fake, m_real, h_real, m_fake, scaling_coef, epsilon, L)
+    return loss

@@ -86,6 +86,57 @@ def gen_loss_full(g):
             print(name, kind, float(loss), flush=True)
 
 
+def _store_grads(d, grads, prefix="grad_"):
+    for n, gr in zip(GRAD_NAMES, grads):
+        a = _np(gr)
+        if a.size > 100000:
+            flat = a.reshape(-1)
+            probe = np.random.default_rng(7).standard_normal(flat.size)
+            d[prefix + n + "_norm"] = float(np.linalg.norm(flat))
+            d[prefix + n + "_stride"] = 997
+            d[prefix + n + "_sample"] = flat[::997].copy()
+            d[prefix + n + "_proj"] = float(flat @ probe)
+        else:
+            d[prefix + n] = a
+
+
+def gen_loss_full_cfg3(g):
+    """BASELINE config 3 at full size (B=64, 2+10 frames of 64x64x3), uniform inputs: the loss alone, and the
+    chain kernel_train.py:270-288 runs with `--kernel 1d`: temporal smoothing (sigma = 5) of real and fake, then
+    the loss on the smoothed tensors, gradients back to the UNSMOOTHED inputs."""
+    from kccotgan_b200.synthetic import CONFIGS
+    KS = ref_exec.load_kernel_smoothing()
+    ks = KS(temporal_kernel_size=6, spatial_kernel_size=6)
+    c = {k: v for k, v in CONFIGS["cfg3_bair"].items() if k != "nprob"}
+    inp = make_inputs(J=8, kind="uniform", seed=1, **c)
+    loss, grads, terms, C = _loss_case(g, inp, torch.float64)
+    d = dict(loss=float(loss), scaling_coef=S, kind="uniform", seed=1, J=8, **c)
+    d.update({k: float(v) for k, v in terms.items()})
+    d.update({k: _np(v) for k, v in C.items()})
+    _store_grads(d, grads)
+    del grads, C
+    # smoothing -> loss
+    leaves = [inp[k].to(torch.float64).clone().requires_grad_(True) for k in INPUT_ORDER]
+    r, f, hf, mr, hr, mf = leaves
+    rs, fs = ks.temporal_convolution(r, 5.0), ks.temporal_convolution(f, 5.0)
+    loss_s = g.compute_sinkhorn_loss(rs, fs, S, 0.8, 100, hf, mr, hr, mf, video=True)
+    grads_s = torch.autograd.grad(loss_s, leaves)
+    d["smooth1d_loss"] = float(loss_s)
+    d["smooth1d_sigma"] = 5.0
+    with torch.no_grad():
+        rt = rs.permute(0, 2, 1, 3, 4).reshape(rs.shape[0], rs.shape[2], -1)
+        ft = fs.permute(0, 2, 1, 3, 4).reshape(fs.shape[0], fs.shape[2], -1)
+        d["smooth1d_loss_xy"] = float(g.compute_sinkhorn(rt, ft, hf, mr, S))
+        d["smooth1d_loss_xx"] = float(g.compute_sinkhorn(rt, rt, hr, mr, S))
+        d["smooth1d_loss_yy"] = float(g.compute_sinkhorn(ft, ft, hf, mf, S))
+        flat = _np(fs).reshape(-1)
+        d["smooth1d_fake_sample"] = flat[::997].copy()
+        d["smooth1d_fake_norm"] = float(np.linalg.norm(flat))
+    _store_grads(d, grads_s, prefix="smooth1d_grad_")
+    np.savez_compressed(os.path.join(OUT, "loss_cfg3_bair_full_uniform.npz"), **d)
+    print("cfg3 full", float(loss), float(loss_s), flush=True)
+
+
 def gen_gan_utils_small(g):
     """Every gan_utils function (rows a1-a8 of SURVEY §8) on one tiny case, plus the quirk KATs."""
     torch.manual_seed(11)
@@ -175,11 +226,15 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_default_dtype(torch.float64)   # the reference's tf.float32 -> fp64 (see tf_shim)
     g = ref_exec.load_gan_utils()
+    if "--only-cfg3" in sys.argv:
+        gen_loss_full_cfg3(g)
+        return
     gen_gan_utils_small(g)
     gen_smoothing()
     gen_loss_reduced(g)
     if "--no-full" not in sys.argv:
         gen_loss_full(g)
+        gen_loss_full_cfg3(g)
 
 
 if __name__ == "__main__":
