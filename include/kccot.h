@@ -117,7 +117,9 @@ int kccot_sinkhorn_bwd(const float* C, int nsolve, int B, float eps, int L, cons
                        void* ws, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
- * Row-sharded single problem (BASELINE config 5).  This rank owns rows
+ * Row-sharded Sinkhorn, host-driven variant (round 1; kept for callers that bring their own exchange): one call
+ * per half-iteration pair, the CALLER moves the column statistics between ranks.  The fused variant below
+ * (kccot_shard_sinkhorn_*) supersedes it.  This rank owns rows
  * [row0, row0+Brows) of the B x B cost (Crows [Brows,B]).  The u-update is local; the v-update needs a
  * column log-sum-exp over all rows: each rank produces colstat [2,B] = (max, sum exp2(. - max)) over its
  * rows, the CALLER all-gathers them (NCCL over NVLink) and every rank combines.  The reverse pass
@@ -137,6 +139,45 @@ int kccot_shard_bwd_seed(const float* Crows, int Brows, int B, float eps, const 
 int kccot_shard_bwd_rows(const float* Crows, int Brows, int B, float eps, const float* u_k_rows,
                          const float* v_k, const float* v_km1, const float* vbar, int first,
                          float* ubar_rows, float* Cbar_rows, float* colsum, void* ws, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Row-sharded mixed loss, fused exchange (BASELINE config 5 on N GPUs).  Videos, h and M are replicated on
+ * every rank (or all-gathered once by the caller); this rank owns the samples [row0, row0 + Brows): it
+ * computes the cost ROWS of the xy, xx, yy blocks (C3rows [3,Brows,B]), runs its row block of the three
+ * Sinkhorn solves inside ONE persistent kernel that exchanges the [B] column sums with the other ranks through
+ * peer-mapped mailboxes (no host-launched collective per iteration), and returns the gradient rows of its
+ * own samples.  Collectives left to the caller, once per evaluation: MIN of `shift` [3] after
+ * kccot_shard_local_min, SUM of cost_partial [3,2] (cost_n = partial[n,1] * eps / log2(e) + shift[n] *
+ * partial[n,0]), all-to-all of the Cbar_xy / Cbar_yy row panels into column panels XYcol, YYcol [B,Brows],
+ * SUM of the two M-gradient partials.
+ *   mbox_ptrs[r] / flag_ptrs[r]: device pointers (valid on THIS device) to rank r's mailbox
+ *   (kccot_shard_mailbox_bytes) and flag array (nranks x uint64, zeroed once).  epoch_base: any number larger
+ *   than every epoch used so far, identical on all ranks (e.g. launch counter << 24).
+ * ------------------------------------------------------------------------------------------ */
+size_t kccot_shard_cost_workspace_bytes(int B, long long K, int Brows);
+int kccot_shard_cost_fwd(const float* real, const float* fake, int B, long long K, int row0, int Brows,
+                         const float* h_fake, const float* m_real, const float* h_real,
+                         const float* m_fake, int T, int J, float s, float* C3rows, void* ws,
+                         size_t ws_bytes, void* stream);
+/* `ws` must be the workspace of the matching kccot_shard_cost_fwd call (it carries the transposed split). */
+int kccot_shard_cost_bwd(const float* Cbar3rows, const float* XYcol, const float* YYcol, int B, long long K,
+                         int row0, int Brows, const float* h_fake, const float* m_real,
+                         const float* h_real, const float* m_fake, int T, int J, float s,
+                         float* g_fake_rows, float* gh_fake_rows, float* gm_real_part,
+                         float* gh_real_rows, float* gm_fake_part, void* ws, size_t ws_bytes, void* stream);
+size_t kccot_shard_sinkhorn_workspace_bytes(int np, int Brows, int B, int L);
+size_t kccot_shard_mailbox_bytes(int np, int nranks, int B);
+int kccot_shard_local_min(const float* Crows, int np, int Brows, int B, float* shift_out, void* stream);
+int kccot_shard_sinkhorn_fwd(const float* Crows, int np, int Brows, int B, int row0, float eps, int L,
+                             int Lmin, float thresh, int exit_on_index, float* u_hist, float* v_hist,
+                             int32_t* nits, float* cost_partial, const float* shift, int nranks, int rank,
+                             void* const* mbox_ptrs, void* const* flag_ptrs,
+                             unsigned long long epoch_base, void* ws, size_t ws_bytes, void* stream);
+int kccot_shard_sinkhorn_bwd(const float* Crows, int np, int Brows, int B, int row0, float eps, int L,
+                             const float* u_hist, const float* v_hist, const int32_t* nits,
+                             const float* gcost, float* Cbar_rows, const float* shift, int nranks, int rank,
+                             void* const* mbox_ptrs, void* const* flag_ptrs,
+                             unsigned long long epoch_base, void* ws, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Fused mixed Sinkhorn loss — gan_utils.py:204-227 (compute_sinkhorn_loss) in ONE call per direction:

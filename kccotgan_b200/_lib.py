@@ -42,6 +42,17 @@ SIGNATURES = {
     "kccot_shard_cost_partial": (_I, [_P, _I, _I, _F, _P, _P, _P, _P, _P]),
     "kccot_shard_bwd_seed": (_I, [_P, _I, _I, _F, _P, _P, _F, _P, _P, _P, _P, _P]),
     "kccot_shard_bwd_rows": (_I, [_P, _I, _I, _F, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P]),
+    "kccot_shard_cost_workspace_bytes": (_SZ, [_I, _LL, _I]),
+    "kccot_shard_cost_fwd": (_I, [_P, _P, _I, _LL, _I, _I, _P, _P, _P, _P, _I, _I, _F, _P, _P, _SZ, _P]),
+    "kccot_shard_cost_bwd": (_I, [_P, _P, _P, _I, _LL, _I, _I, _P, _P, _P, _P, _I, _I, _F, _P, _P, _P, _P, _P, _P, _SZ,
+                                  _P]),
+    "kccot_shard_sinkhorn_workspace_bytes": (_SZ, [_I, _I, _I, _I]),
+    "kccot_shard_mailbox_bytes": (_SZ, [_I, _I, _I]),
+    "kccot_shard_local_min": (_I, [_P, _I, _I, _I, _P, _P]),
+    "kccot_shard_sinkhorn_fwd": (_I, [_P, _I, _I, _I, _I, _F, _I, _I, _F, _I, _P, _P, _P, _P, _P, _I, _I, _P, _P,
+                                      _c.c_ulonglong, _P, _SZ, _P]),
+    "kccot_shard_sinkhorn_bwd": (_I, [_P, _I, _I, _I, _I, _F, _I, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P,
+                                      _c.c_ulonglong, _P, _SZ, _P]),
     "kccot_mixed_loss_saved_bytes": (_SZ, [_I, _I, _I]),
     "kccot_mixed_loss_workspace_bytes": (_SZ, [_I, _I, _LL, _I]),
     "kccot_mixed_loss_fwd": (_I, [_P, _P, _I, _I, _LL, _P, _P, _P, _P, _I, _I, _F, _F, _I, _P, _P, _P, _P, _SZ, _I, _P]),

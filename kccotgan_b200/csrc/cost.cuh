@@ -125,6 +125,14 @@ int large_cost_fwd(const float* x, const float* y, int Bx, int By, long long K, 
                    cudaStream_t st);
 int large_cost_bwd(const float* Cbar, const float* x, const float* y, int Bx, int By, long long K, float s, float* gx,
                    float* gy, int accumulate, void* ws, size_t ws_bytes, cudaStream_t st);
+size_t large_shard_ws_bytes(int B, long long K, int Brows);
+int large_shard_cost_fwd(const float* real, const float* fake, int B, long long K, int row0, int Brows, const float* h_fake,
+                         const float* m_real, const float* h_real, const float* m_fake, int T, int J, float s,
+                         float* C3rows, void* ws, size_t ws_bytes, cudaStream_t st);
+int large_shard_cost_bwd(const float* Cbar3rows, const float* XYcol, const float* YYcol, int B, long long K, int row0,
+                         int Brows, const float* h_fake, const float* m_real, const float* h_real, const float* m_fake,
+                         int T, int J, float s, float* g_fake_rows, float* gh_fake_rows, float* gm_real_part,
+                         float* gh_real_rows, float* gm_fake_part, void* ws, size_t ws_bytes, cudaStream_t st);
 void large_set_drain(int k_blocks);
 void large_set_pair(int use_pair);
 

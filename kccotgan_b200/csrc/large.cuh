@@ -26,6 +26,7 @@ struct LargeFinBlock {
   float* C;
   long long ldc;
   int Bx, By, zero_diag;
+  int diag_off;              // the self-distance zero sits at j == i + diag_off (row shards: the block's first global row)
 };
 struct LargeFin {
   LargeFinBlock b[3];
@@ -42,5 +43,10 @@ int large_launch_finalize(const LargeFin& F, int nblocks, int T, int J, float s,
 int large_launch_wbuild(const float* Cxx, const float* Cxy, const float* Cyy, int Bx, int By, int row_off, int nrows,
                         int Rp, float* Wtmp, float* rs_part, float* rowsum, float* scal, __half* Wh1, __half* Wh2,
                         cudaStream_t st);
+// row shard: W' rows of the fake samples [row0, row0 + nloc) from the column panels XYcol [Bx][nloc] = Cbar_xy[:, rows],
+// YYcol [By][nloc] = Cbar_yy[:, rows] (received from the other ranks) and the own rows YYrow [nloc][By] = Cbar_yy[rows, :]
+int large_launch_wbuild_shard(const float* XYcol, const float* YYcol, const float* YYrow, int Bx, int By, int row0, int nloc,
+                              int Rp, float* Wtmp, float* rs_part, float* rowsum, float* scal, __half* Wh1, __half* Wh2,
+                              cudaStream_t st);
 
 }  // namespace kccot

@@ -174,11 +174,11 @@ int large_mixed_cost_fwd(const float* real, const float* fake, int B, long long 
   LargeFin F{};
   // order xy, xx, yy — gan_utils.py:221-223
   F.b[0] = LargeFinBlock{w.P[0], B, w.job[0].ks_stride, w.ksplit, 0, w.norms, w.norms + B, h_fake, m_real, nullptr, nullptr,
-                         C3, B, B, B, 0};
+                         C3, B, B, B, 0, 0};
   F.b[1] = LargeFinBlock{w.P[1], B, w.job[1].ks_stride, w.ksplit, 1, w.norms, w.norms, h_real, m_real, nullptr, nullptr,
-                         C3 + BB, B, B, B, 1};
+                         C3 + BB, B, B, B, 1, 0};
   F.b[2] = LargeFinBlock{w.P[2], B, w.job[2].ks_stride, w.ksplit, 1, w.norms + B, w.norms + B, h_fake, m_fake, nullptr,
-                         nullptr, C3 + 2 * BB, B, B, B, 1};
+                         nullptr, C3 + 2 * BB, B, B, B, 1, 0};
   return large_launch_finalize(F, 3, T, J, s, w.scal, st);
 }
 
@@ -192,7 +192,7 @@ int large_cost_fwd(const float* x, const float* y, int Bx, int By, long long K, 
   if (int rc = run_fwd(w, x, y, Bx, By, K, same, st)) return rc;
   LargeFin F{};
   F.b[0] = LargeFinBlock{w.P[0], By, w.job[0].ks_stride, w.ksplit, same ? 1 : 0, w.norms, same ? w.norms : w.norms + Bx,
-                         h1, M1, h2, M2, C, By, Bx, By, same ? 1 : 0};
+                         h1, M1, h2, M2, C, By, Bx, By, same ? 1 : 0, 0};
   return large_launch_finalize(F, 1, T, J, s, w.scal, st);
 }
 
@@ -224,6 +224,122 @@ int large_cost_bwd(const float* Cbar, const float* x, const float* y, int Bx, in
   if (gy)   // gx == gy (x and y are the same tensor): the second product adds to the first
     if (int rc = run_bwd_rows(w, nullptr, Cbar, nullptr, Bx, By, K, s, Bx, By, gy, accumulate || gy == gx, st)) return rc;
   return KCCOT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Row shards of ONE large problem (BASELINE config 5 on N GPUs).  Inputs (videos, h, M) are replicated; this rank
+// owns the samples [row0, row0 + Brows) and computes the cost ROWS of the three blocks, later the gradient rows.
+// The workspace of the forward call carries the transposed split and the scales to the backward call.
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct ShardWs {
+  float *scal, *part, *mean, *norms, *Wtmp, *rs_part, *rowsum;
+  __half *Zh1, *Zh2, *ZT1, *ZT2, *Wh1, *Wh2;
+  float* P[3];
+  int nseg, Rp;
+  long long Kp;
+  size_t bytes;
+};
+ShardWs carve_shard(void* ws, int B, long long K, int Brows) {
+  ShardWs w{};
+  const int R = 2 * B;
+  w.Kp = pad64(K);
+  w.Rp = (int)pad64(R);
+  w.nseg = stats_segments(R, K);
+  Carver c(ws);
+  w.scal = c.take<float>(kScalCount);
+  w.part = c.take<float>((size_t)w.nseg * K);
+  w.mean = c.take<float>((size_t)w.Kp);
+  w.norms = c.take<float>((size_t)R);
+  w.Zh1 = c.take<__half>((size_t)R * w.Kp);
+  w.Zh2 = c.take<__half>((size_t)R * w.Kp);
+  w.ZT1 = c.take<__half>((size_t)w.Kp * w.Rp);
+  w.ZT2 = c.take<__half>((size_t)w.Kp * w.Rp);
+  for (int q = 0; q < 3; ++q) w.P[q] = c.take<float>((size_t)Brows * B);
+  w.Wtmp = c.take<float>((size_t)Brows * w.Rp);
+  w.rs_part = c.take<float>((size_t)((R + 31) / 32) * Brows);
+  w.rowsum = c.take<float>((size_t)Brows);
+  w.Wh1 = c.take<__half>((size_t)Brows * w.Rp);
+  w.Wh2 = c.take<__half>((size_t)Brows * w.Rp);
+  w.bytes = align_up(c.off, 256);
+  return w;
+}
+}  // namespace
+
+size_t large_shard_ws_bytes(int B, long long K, int Brows) { return carve_shard(nullptr, B, K, Brows).bytes; }
+
+int large_shard_cost_fwd(const float* real, const float* fake, int B, long long K, int row0, int Brows, const float* h_fake,
+                         const float* m_real, const float* h_real, const float* m_fake, int T, int J, float s,
+                         float* C3rows, void* ws, size_t ws_bytes, cudaStream_t st) {
+  KCCOT_CHECK_ARG(row0 >= 0 && Brows >= 1 && row0 + Brows <= B, "bad row range [%d, %d) of %d", row0, row0 + Brows, B);
+  const ShardWs w = carve_shard(ws, B, K, Brows);
+  KCCOT_CHECK_ARG(ws_bytes >= w.bytes, "workspace too small (row-shard cost path needs %zu bytes, got %zu)", w.bytes, ws_bytes);
+  const int R = 2 * B;
+  if (int rc = large_launch_stats(real, fake, B, B, K, w.nseg, w.part, w.mean, w.scal, st)) return rc;
+  if (int rc = large_launch_split(real, fake, B, B, K, w.Kp, w.Rp, w.mean, w.scal, w.Zh1, w.Zh2, w.ZT1, w.ZT2, st)) return rc;
+  if (int rc = large_launch_rownorm(w.Zh1, w.Zh2, R, K, w.Kp, w.norms, st)) return rc;
+  G3Params P{};
+  // xy: real rows x all fakes; xx: real rows x all reals; yy: fake rows x all fakes (no symmetry across ranks)
+  P.job[0] = G3Job{row0, B, Brows, B, 0, 0, 0, 0, w.P[0], B, 0};
+  P.job[1] = G3Job{row0, 0, Brows, B, 0, 0, 0, 0, w.P[1], B, 0};
+  P.job[2] = G3Job{B + row0, B, Brows, B, 0, 0, 0, 0, w.P[2], B, 0};
+  P.njobs = 3;
+  int ntiles = 0;
+  for (int j = 0; j < 3; ++j) ntiles += g_pair ? g3_count_tiles_pair(&P.job[j]) : g3_count_tiles(&P.job[j]);
+  (void)ntiles;
+  P.ksplit = 1;
+  P.kb_per_split = (int)(w.Kp / G3_BK);
+  P.drain = g_drain;
+  P.alpha = 1.f;
+  if (int rc = g_pair ? launch_gemm_f16x3_pair(w.Zh1, w.Zh2, R, w.Kp, w.Zh1, w.Zh2, R, w.Kp, K, P, st)
+                      : launch_gemm_f16x3(w.Zh1, w.Zh2, R, w.Kp, w.Zh1, w.Zh2, R, w.Kp, K, P, st))
+    return rc;
+  const long long RB = (long long)Brows * B, hm = (long long)T * J;
+  LargeFin F{};
+  F.b[0] = LargeFinBlock{w.P[0], B, RB, 1, 0, w.norms + row0, w.norms + B, h_fake + row0 * hm, m_real, nullptr, nullptr,
+                         C3rows, B, Brows, B, 0, 0};
+  F.b[1] = LargeFinBlock{w.P[1], B, RB, 1, 0, w.norms + row0, w.norms, h_real + row0 * hm, m_real, nullptr, nullptr,
+                         C3rows + RB, B, Brows, B, 1, row0};
+  F.b[2] = LargeFinBlock{w.P[2], B, RB, 1, 0, w.norms + B + row0, w.norms + B, h_fake + row0 * hm, m_fake, nullptr, nullptr,
+                         C3rows + 2 * RB, B, Brows, B, 1, row0};
+  return large_launch_finalize(F, 3, T, J, s, w.scal, st);
+}
+
+// g_fake_rows [Brows][K]; gh_* rows [Brows][T][J] (own samples); gm_* partial sums [B][T][J] over this rank's rows
+// (the caller all-reduces them).  `ws` is the workspace of the matching large_shard_cost_fwd call.
+int large_shard_cost_bwd(const float* Cbar3rows, const float* XYcol, const float* YYcol, int B, long long K, int row0,
+                         int Brows, const float* h_fake, const float* m_real, const float* h_real, const float* m_fake,
+                         int T, int J, float s, float* g_fake_rows, float* gh_fake_rows, float* gm_real_part,
+                         float* gh_real_rows, float* gm_fake_part, void* ws, size_t ws_bytes, cudaStream_t st) {
+  const ShardWs w = carve_shard(ws, B, K, Brows);
+  KCCOT_CHECK_ARG(ws_bytes >= w.bytes, "workspace too small (row-shard cost path needs %zu bytes, got %zu)", w.bytes, ws_bytes);
+  const long long RB = (long long)Brows * B, hm = (long long)T * J;
+  const float *Cxy = Cbar3rows, *Cxx = Cbar3rows + RB, *Cyy = Cbar3rows + 2 * RB;
+  // martingale adjoints (gan_utils.py:34-38): h gradients belong to the row samples (local), M gradients to the
+  // column samples (partial over this rank's rows)
+  MartJobs jobs{};
+  jobs.j[0] = MartJob{gh_fake_rows, Cxy, m_real, Cyy, m_fake, 0, B, Brows, B, 0, 0, 0};
+  jobs.j[1] = MartJob{gm_real_part, Cxy, h_fake + row0 * hm, Cxx, h_real + row0 * hm, 0, B, B, Brows, 1, 1, 0};
+  jobs.j[2] = MartJob{gh_real_rows, Cxx, m_real, nullptr, nullptr, 0, B, Brows, B, 0, 0, 0};
+  jobs.j[3] = MartJob{gm_fake_part, Cyy, h_fake + row0 * hm, nullptr, nullptr, 0, B, B, Brows, 1, 1, 0};
+  if (int rc = launch_martingale_jobs(jobs, 4, 1, T, J, s, st)) return rc;
+  if (!g_fake_rows) return KCCOT_OK;
+  if (int rc = large_launch_wbuild_shard(XYcol, YYcol, Cyy, B, B, row0, Brows, w.Rp, w.Wtmp, w.rs_part, w.rowsum, w.scal,
+                                         w.Wh1, w.Wh2, st))
+    return rc;
+  G3Params P{};
+  P.job[0] = G3Job{0, 0, Brows, (int)K, 0, 0, 0, 0, g_fake_rows, K, 0};
+  if (g_pair) g3_count_tiles_pair(&P.job[0]);
+  else g3_count_tiles(&P.job[0]);
+  P.njobs = 1;
+  P.ksplit = 1;
+  P.kb_per_split = (int)(w.Rp / G3_BK);
+  P.drain = g_drain;
+  P.alpha = -2.f * s;
+  P.alpha_dev = w.scal + kScalGradAlpha;
+  const int R = 2 * B;
+  if (g_pair) return launch_gemm_f16x3_pair(w.Wh1, w.Wh2, Brows, w.Rp, w.ZT1, w.ZT2, K, w.Rp, R, P, st);
+  return launch_gemm_f16x3(w.Wh1, w.Wh2, Brows, w.Rp, w.ZT1, w.ZT2, K, w.Rp, R, P, st);
 }
 
 }  // namespace kccot

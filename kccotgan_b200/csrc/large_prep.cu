@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(256) large_finalize_kernel(LargeFin F, int T, 
       const int j = j0 + tx * 4 + c;
       if (j >= b.By) continue;
       float out;
-      if (b.zero_diag && i == j) {
+      if (b.zero_diag && i + b.diag_off == j) {
         out = s * mart[a][c];
       } else {
         double d = 0.0;
@@ -287,8 +287,15 @@ __global__ void __launch_bounds__(256) large_finalize_kernel(LargeFin F, int T, 
 struct WSrc {
   const float *Cxx, *Cxy, *Cyy;
   int Bx, By;
+  // row-shard mode (XYcol != nullptr): only fake rows [row0, row0 + nloc) exist, as column panels / own rows
+  const float *XYcol, *YYcol, *YYrow;
+  int row0, nloc;
 };
 __device__ __forceinline__ float w_direct(const WSrc& S, int r, int c) {
+  if (S.XYcol != nullptr) {
+    if (c < S.Bx) return 0.f;
+    return S.YYrow[(long long)(r - S.Bx - S.row0) * S.By + (c - S.Bx)];
+  }
   if (r < S.Bx) {
     if (c < S.Bx) return S.Cxx ? S.Cxx[(long long)r * S.Bx + c] : 0.f;
     return S.Cxy[(long long)r * S.By + (c - S.Bx)];
@@ -297,6 +304,11 @@ __device__ __forceinline__ float w_direct(const WSrc& S, int r, int c) {
   return S.Cyy ? S.Cyy[(long long)(r - S.Bx) * S.By + (c - S.Bx)] : 0.f;
 }
 __device__ __forceinline__ float w_transposed(const WSrc& S, int r, int c) {
+  if (S.XYcol != nullptr) {
+    const int jl = r - S.Bx - S.row0;
+    if (c < S.Bx) return S.XYcol[(long long)c * S.nloc + jl];
+    return S.YYcol[(long long)(c - S.Bx) * S.nloc + jl];
+  }
   if (r < S.Bx) {
     if (c < S.Bx) return S.Cxx ? S.Cxx[(long long)c * S.Bx + r] : 0.f;
     return 0.f;
@@ -415,7 +427,7 @@ int large_launch_wbuild(const float* Cxx, const float* Cxy, const float* Cyy, in
                         cudaStream_t st) {
   const int R = Bx + By;
   const int nct = (R + 31) / 32;
-  WSrc S{Cxx, Cxy, Cyy, Bx, By};
+  WSrc S{Cxx, Cxy, Cyy, Bx, By, nullptr, nullptr, nullptr, 0, 0};
   unsigned* sb = reinterpret_cast<unsigned*>(scal);
   KCCOT_CUDA(cudaMemsetAsync(sb + kScalWabs, 0, 2 * sizeof(unsigned), st));
   w_tiles_kernel<<<dim3(nct, (nrows + 31) / 32), dim3(32, 8), 0, st>>>(S, row_off, nrows, Rp, Wtmp, rs_part, sb + kScalWabs);
@@ -423,6 +435,24 @@ int large_launch_wbuild(const float* Cxx, const float* Cxy, const float* Cyy, in
   w_rowsum_kernel<<<(nrows + 255) / 256, 256, 0, st>>>(rs_part, nct, nrows, rowsum, sb + kScalDabs);
   KCCOT_LAUNCH_CHECK();
   w_convert_kernel<<<dim3((R + 255) / 256, nrows), 256, 0, st>>>(Wtmp, rowsum, scal, row_off, R, Rp, Wh1, Wh2);
+  KCCOT_LAUNCH_CHECK();
+  return KCCOT_OK;
+}
+
+int large_launch_wbuild_shard(const float* XYcol, const float* YYcol, const float* YYrow, int Bx, int By, int row0, int nloc,
+                              int Rp, float* Wtmp, float* rs_part, float* rowsum, float* scal, __half* Wh1, __half* Wh2,
+                              cudaStream_t st) {
+  const int R = Bx + By;
+  const int nct = (R + 31) / 32;
+  const int row_off = Bx + row0;                       // stacked index of the first wanted row
+  WSrc S{nullptr, nullptr, nullptr, Bx, By, XYcol, YYcol, YYrow, row0, nloc};
+  unsigned* sb = reinterpret_cast<unsigned*>(scal);
+  KCCOT_CUDA(cudaMemsetAsync(sb + kScalWabs, 0, 2 * sizeof(unsigned), st));
+  w_tiles_kernel<<<dim3(nct, (nloc + 31) / 32), dim3(32, 8), 0, st>>>(S, row_off, nloc, Rp, Wtmp, rs_part, sb + kScalWabs);
+  KCCOT_LAUNCH_CHECK();
+  w_rowsum_kernel<<<(nloc + 255) / 256, 256, 0, st>>>(rs_part, nct, nloc, rowsum, sb + kScalDabs);
+  KCCOT_LAUNCH_CHECK();
+  w_convert_kernel<<<dim3((R + 255) / 256, nloc), 256, 0, st>>>(Wtmp, rowsum, scal, row_off, R, Rp, Wh1, Wh2);
   KCCOT_LAUNCH_CHECK();
   return KCCOT_OK;
 }

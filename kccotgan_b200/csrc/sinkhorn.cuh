@@ -46,8 +46,9 @@ int stream_sinkhorn_bwd(const float* C, int B, float eps, int L, const float* u_
 constexpr int kMaxShardRanks = 8;
 struct ShardComm {
   int nranks, rank;
-  float* mbox[kMaxShardRanks];        // mailbox of every rank (device pointers valid on THIS device)
-  unsigned* flags[kMaxShardRanks];    // epoch flags of every rank, [nranks] each
+  float* mbox[kMaxShardRanks];                 // mailbox of every rank (device pointers valid on THIS device)
+  unsigned long long* flags[kMaxShardRanks];   // epoch flags of every rank, [nranks] each, zero before first use
+  unsigned long long epoch0;                   // fresh for every launch and larger than any epoch used before
 };
 bool persist_supported(int Brows, int B, int L);
 size_t persist_workspace_bytes(int np, int Brows, int B, int L);

@@ -59,12 +59,12 @@ __device__ __forceinline__ float ldcg_f(const float* p) { return __ldcg(p); }
 __device__ __forceinline__ float4 ldcg_f4(const float4* p) { return __ldcg(p); }
 __device__ __forceinline__ int ld_volatile_i(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
 
-__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
@@ -123,8 +123,9 @@ __device__ __forceinline__ Geo make_geo(int np, int Brows, int B) {
 // Called by ALL CTAs of the grid the same number of times (it contains grid barriers).
 struct Xchg {
   int nranks, rank;
-  float* mbox[kMaxShardRanks];          // every rank's mailbox [2][np][nranks][2][nv4 * 4] (peer-mapped)
-  unsigned* flags[kMaxShardRanks];      // every rank's epoch flags [nranks]
+  float* mbox[kMaxShardRanks];              // every rank's mailbox [2][np][nranks][2][nv4 * 4] (peer-mapped)
+  unsigned long long* flags[kMaxShardRanks];   // every rank's epoch flags [nranks]; epochs grow monotonically over
+  unsigned long long epoch0;                   // launches (the caller passes a fresh base per launch), never reset
 };
 
 __device__ __forceinline__ size_t mbox_off(int parity, int np, int p, int nranks, int r, int vec, int nv4) {
@@ -132,14 +133,14 @@ __device__ __forceinline__ size_t mbox_off(int parity, int np, int p, int nranks
 }
 
 // phase A: push this rank's combined local granule to every rank's mailbox
-__device__ __forceinline__ void xchg_push(const Xchg& X, unsigned epoch, int np, int p, int nv4, int gi, int vec, float4 v) {
+__device__ __forceinline__ void xchg_push(const Xchg& X, unsigned long long epoch, int np, int p, int nv4, int gi, int vec, float4 v) {
   for (int r = 0; r < X.nranks; ++r) {
-    float4* dst = reinterpret_cast<float4*>(X.mbox[r] + mbox_off(epoch & 1, np, p, X.nranks, X.rank, vec, nv4)) + gi;
+    float4* dst = reinterpret_cast<float4*>(X.mbox[r] + mbox_off((int)(epoch & 1), np, p, X.nranks, X.rank, vec, nv4)) + gi;
     *dst = v;
   }
 }
 // between phase A and B: two grid barriers around the flag handshake of CTA 0
-__device__ __forceinline__ void xchg_sync(cg::grid_group& grid, const Xchg& X, unsigned epoch, PState* st) {
+__device__ __forceinline__ void xchg_sync(cg::grid_group& grid, const Xchg& X, unsigned long long epoch, PState* st) {
   __threadfence_system();
   grid.sync();
   if (blockIdx.x == 0 && threadIdx.x < X.nranks && (int)threadIdx.x != X.rank) {
@@ -217,6 +218,7 @@ struct PFwd {
   float* bvec;           // [np][B]
   PState* state;         // [np]
   int np, Brows, B, row0, L, Lmin, exit_on_index, resident, shift_stride, Gmax;
+  int partial_cost;      // write the (s0, s1) sums of this rank's rows instead of the finished cost
   float kscale, ahat, thresh;
   Xchg X;
 };
@@ -262,7 +264,7 @@ __global__ void __launch_bounds__(kNT, 1) sk_persist_fwd_kernel(const __grid_con
   for (int c = 0; c < CPT; ++c) { b[c] = 1.f; tcol[c] = 0.f; cmx[c] = kNegBig; }
   int it = 0, mode = 0, parity = 0;
   bool done = false;
-  unsigned epoch = 0;
+  unsigned long long epoch = P.X.epoch0;
 
   for (;;) {
     // ------------------------------------------------------------------ row pass
@@ -464,18 +466,18 @@ __global__ void __launch_bounds__(kNT, 1) sk_persist_fwd_kernel(const __grid_con
           if (mode == 0 || gi == G.nv4 - 1) {
             A = make_float4(0.f, 0.f, 0.f, 0.f);
             for (int r = 0; r < P.X.nranks; ++r) {
-              const float4 v = ldcg_f4(reinterpret_cast<const float4*>(mb + mbox_off(epoch & 1, P.np, p, P.X.nranks, r, 0, G.nv4)) + gi);
+              const float4 v = ldcg_f4(reinterpret_cast<const float4*>(mb + mbox_off((int)(epoch & 1), P.np, p, P.X.nranks, r, 0, G.nv4)) + gi);
               A.x += v.x; A.y += v.y; A.z += v.z; A.w += v.w;
             }
           } else {
             A = make_float4(kNegBig, kNegBig, kNegBig, kNegBig);
             for (int r = 0; r < P.X.nranks; ++r) {
-              const float4 v = ldcg_f4(reinterpret_cast<const float4*>(mb + mbox_off(epoch & 1, P.np, p, P.X.nranks, r, 0, G.nv4)) + gi);
+              const float4 v = ldcg_f4(reinterpret_cast<const float4*>(mb + mbox_off((int)(epoch & 1), P.np, p, P.X.nranks, r, 0, G.nv4)) + gi);
               A.x = fmaxf(A.x, v.x); A.y = fmaxf(A.y, v.y); A.z = fmaxf(A.z, v.z); A.w = fmaxf(A.w, v.w);
             }
             for (int r = 0; r < P.X.nranks; ++r) {
-              const float4 m = ldcg_f4(reinterpret_cast<const float4*>(mb + mbox_off(epoch & 1, P.np, p, P.X.nranks, r, 0, G.nv4)) + gi);
-              const float4 s = ldcg_f4(reinterpret_cast<const float4*>(mb + mbox_off(epoch & 1, P.np, p, P.X.nranks, r, 1, G.nv4)) + gi);
+              const float4 m = ldcg_f4(reinterpret_cast<const float4*>(mb + mbox_off((int)(epoch & 1), P.np, p, P.X.nranks, r, 0, G.nv4)) + gi);
+              const float4 s = ldcg_f4(reinterpret_cast<const float4*>(mb + mbox_off((int)(epoch & 1), P.np, p, P.X.nranks, r, 1, G.nv4)) + gi);
               Bv.x += s.x * fast_exp2(m.x - A.x); Bv.y += s.y * fast_exp2(m.y - A.y);
               Bv.z += s.z * fast_exp2(m.z - A.z); Bv.w += s.w * fast_exp2(m.w - A.w);
             }
@@ -559,7 +561,7 @@ __global__ void __launch_bounds__(kNT, 1) sk_persist_fwd_kernel(const __grid_con
       s0 += ldcg_f(pa + (long long)c * G.nv4 * 4);
       s1 += ldcg_f(pa + (long long)c * G.nv4 * 4 + 1);
     }
-    if (P.X.nranks > 1) {                 // partial sums of this rank's rows; the caller all-reduces them
+    if (P.partial_cost) {                 // partial sums of this rank's rows; the caller all-reduces them
       P.cost[2 * p] = s0;
       P.cost[2 * p + 1] = s1;
     } else {
@@ -626,7 +628,7 @@ __global__ void __launch_bounds__(kNT, 1) sk_persist_bwd_kernel(const __grid_con
 #pragma unroll
   for (int m = 0; m < NG; ++m) colok[m] = 4 * (tid + kNT * m) < B;
   int parity = 0;
-  unsigned epoch = 0;
+  unsigned long long epoch = P.X.epoch0;
   const bool multi = P.X.nranks > 1;
 
   if (P.resident) {
@@ -660,7 +662,7 @@ __global__ void __launch_bounds__(kNT, 1) sk_persist_bwd_kernel(const __grid_con
     if (owner) {
       float tsum = 0.f;
       for (int r = 0; r < P.X.nranks; ++r)
-        tsum += ldcg_f(P.X.mbox[P.X.rank] + mbox_off(epoch & 1, P.np, p, P.X.nranks, r, 0, G.nv4) + (size_t)(G.nv4 - 1) * 4);
+        tsum += ldcg_f(P.X.mbox[P.X.rank] + mbox_off((int)(epoch & 1), P.np, p, P.X.nranks, r, 0, G.nv4) + (size_t)(G.nv4 - 1) * 4);
       if (tsum > 0.f) st->trip = 1;
     }
     grid.sync();
@@ -708,7 +710,7 @@ __global__ void __launch_bounds__(kNT, 1) sk_persist_bwd_kernel(const __grid_con
       for (int gi = G.g_begin + tid; gi < min(G.g_end, B / 4); gi += kNT) {
         float4 A = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int r = 0; r < P.X.nranks; ++r) {
-          const float4 v = ldcg_f4(reinterpret_cast<const float4*>(mb + mbox_off(epoch & 1, P.np, p, P.X.nranks, r, 0, G.nv4)) + gi);
+          const float4 v = ldcg_f4(reinterpret_cast<const float4*>(mb + mbox_off((int)(epoch & 1), P.np, p, P.X.nranks, r, 0, G.nv4)) + gi);
           A.x += v.x; A.y += v.y; A.z += v.z; A.w += v.w;
         }
         fin(gi, A);
@@ -1046,9 +1048,10 @@ int persist_sinkhorn_fwd(const float* C, int np, int Brows, int B, int row0, flo
   P.np = np; P.Brows = Brows; P.B = B; P.row0 = row0; P.L = L; P.Lmin = Lmin; P.exit_on_index = exit_on_index;
   P.shift_stride = 1; P.Gmax = l.Gmax;
   P.kscale = kscale; P.ahat = ahat; P.thresh = thresh;
-  P.X.nranks = 1; P.X.rank = 0;
+  P.X.nranks = 1; P.X.rank = 0; P.X.epoch0 = 0;
+  P.partial_cost = comm ? 1 : 0;
   if (comm) {
-    P.X.nranks = comm->nranks; P.X.rank = comm->rank;
+    P.X.nranks = comm->nranks; P.X.rank = comm->rank; P.X.epoch0 = comm->epoch0;
     for (int r = 0; r < comm->nranks; ++r) { P.X.mbox[r] = comm->mbox[r]; P.X.flags[r] = comm->flags[r]; }
   }
   const int grid = min(num_sms(), np * Brows);
@@ -1097,9 +1100,9 @@ int persist_sinkhorn_bwd(const float* C, int np, int Brows, int B, int row0, flo
   P.state = state;
   P.np = np; P.Brows = Brows; P.B = B; P.row0 = row0; P.L = L; P.shift_stride = 1; P.Gmax = l.Gmax;
   P.kscale = kscale; P.ahat = ahat; P.inv_eps = 1.f / eps;
-  P.X.nranks = 1; P.X.rank = 0;
+  P.X.nranks = 1; P.X.rank = 0; P.X.epoch0 = 0;
   if (comm) {
-    P.X.nranks = comm->nranks; P.X.rank = comm->rank;
+    P.X.nranks = comm->nranks; P.X.rank = comm->rank; P.X.epoch0 = comm->epoch0;
     for (int r = 0; r < comm->nranks; ++r) { P.X.mbox[r] = comm->mbox[r]; P.X.flags[r] = comm->flags[r]; }
   }
   const int grid = min(num_sms(), np * Brows);
