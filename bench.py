@@ -177,6 +177,16 @@ class Ctx:
     pass
 
 
+_T0 = time.perf_counter()
+
+
+def progress(msg):
+    """Progress on stderr (the JSON line is the only thing on stdout)."""
+    if int(os.environ.get("RANK", "0")) == 0:
+        sys.stderr.write(f"[bench +{time.perf_counter() - _T0:6.1f}s] {msg}\n")
+        sys.stderr.flush()
+
+
 def barrier(cx):
     cx.torch.cuda.synchronize()
     if cx.world > 1:
@@ -197,6 +207,9 @@ def timed(cx, fn, steps, warmup=3):
     torch = cx.torch
     for i in range(warmup):
         fn(i)
+        if os.environ.get("KCCOT_BENCH_SYNC"):              # debugging aid: find the call that does not come back
+            torch.cuda.synchronize()
+            progress(f"warm-up call {i} done")
     barrier(cx)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
@@ -353,11 +366,16 @@ def run_cfg4(cx, kind, steps):
             return loss, torch.autograd.grad(loss, t[1:], grad_outputs=ones)
         return step
     fns = [make_step(t) for t in sets]
+    progress(f"cfg4: {P} problems on this rank, {nsets} input sets; capturing")
     replays = [capture(cx, fn)[0] for fn in fns]
+    progress("cfg4: captured")
     use_graph = all(r is not None for r in replays)
     n0 = cx.lib.kccot_launch_count()
     loss0, _ = fns[0]()
     per_step = int(cx.lib.kccot_launch_count() - n0)
+    if os.environ.get("KCCOT_BENCH_SYNC"):
+        torch.cuda.synchronize()
+        progress("cfg4: eager call done")
     run = (lambda i: replays[i % nsets]()) if use_graph else (lambda i: fns[i % nsets]())
     ms, clocks = timed(cx, run, steps)
     value = nprob_total * steps / (ms * 1e-3)
@@ -539,6 +557,7 @@ def main():
         grads = torch.autograd.grad(loss, leaves[1:])
         return loss, grads
 
+    progress(f"headline {args.workload}: {nsets} input sets ready")
     for i in range(max(3, args.warmup)):
         step(sets[i % nsets])
     barrier(cx)
@@ -560,6 +579,7 @@ def main():
     else:
         notes["launch"] = "eager Python calls (gan_utils.compute_sinkhorn_loss + torch.autograd.grad)"
 
+    progress("graphs captured; timing the headline")
     launches0 = lib.kccot_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier(cx)
@@ -592,6 +612,7 @@ def main():
         barrier(cx)
         eager_evals = world * ne / (max_over_ranks(cx, e0.elapsed_time(e1)) * 1e-3)
 
+    progress(f"headline {value:.0f} evals/s; eager + e2e legs")
     # ---- e2e: host (pinned) inputs through the public API, H2D + D2H inside the timed region
     host = [[t.detach().cpu().pin_memory() for t in sets[i]] for i in range(min(nsets, 3))]
     h2d = sum(t.numel() * 4 for t in host[0])
@@ -651,7 +672,10 @@ def main():
     other = {}
     wanted = [c for c in args.configs.split(",") if c]
     few = max(3, min(args.steps, 200))
+    import faulthandler
     for name in wanted:
+        progress(f"config {name}")
+        faulthandler.dump_traceback_later(int(os.environ.get("KCCOT_BENCH_TB", "240")), exit=False)   # a stuck leg leaves its Python stack on stderr
         try:
             if name == "cfg1_mmnist":
                 other[name] = run_replica_config(cx, name, args.kind, few, smooth=False)
@@ -663,6 +687,7 @@ def main():
                 other[name] = run_cfg5(cx, args.kind, max(2, min(args.steps, 5)))
         except Exception as e:                       # a failing side config must not take the headline down
             other[name] = {"error": f"{type(e).__name__}: {e}"}
+        faulthandler.cancel_dump_traceback_later()
         torch.cuda.empty_cache()
 
     if rank != 0:
@@ -670,6 +695,7 @@ def main():
             dist.destroy_process_group()
         return
 
+    progress("stage times, CPU baseline")
     # ---- per-stage device times + roofline of the dominant HBM kernel (rank 0, after the timed region)
     pk = peaks()
     hbm_peak = float(pk.get("hbm_gbs", 6650.0))

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <atomic>
 
 #include "../../include/kccot.h"
@@ -64,6 +65,19 @@ inline bool smem_attr_needed(size_t (&cache)[kMaxDevices], size_t want) {
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// Programmatic launches are used only for the latency-bound chains of a FEW problems.  With hundreds of problems per
+// call the Sinkhorn kernels run in several waves, nothing is gained from overlapping prologues, and on B200 /
+// CUDA 12.9 queued CUDA-graph replays of such a chain stopped making progress (nprob >= 150 hung, nprob <= 64 ran;
+// the same graphs without the launch attribute ran).  The C-ABI entry points open a PdlScope with their problem
+// count; launch_pdl() degrades to a plain launch outside the limit.
+constexpr int kPdlMaxProblems = 16;
+extern thread_local bool t_pdl_ok;
+struct PdlScope {
+  bool prev;
+  explicit PdlScope(bool ok) : prev(t_pdl_ok) { t_pdl_ok = t_pdl_ok && ok; }
+  ~PdlScope() { t_pdl_ok = prev; }
+};
+
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
                               Args... args) {
@@ -76,7 +90,11 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = t_pdl_ok ? 1 : 0;
+#ifdef KCCOT_DEV
+  static const bool no_pdl = getenv("KCCOT_NO_PDL") != nullptr;      // development build: A/B switch
+  if (no_pdl) cfg.numAttrs = 0;
+#endif
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 int num_sms();

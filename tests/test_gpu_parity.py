@@ -581,3 +581,42 @@ def test_sharded_kernels_two_virtual_ranks():
     Cb = cf.sinkhorn_backward(C.astype(np.float64), eps, ruh, rvh, n, gbar=g)
     assert abs(cost - ref) <= LOSS_TOL * abs(ref)
     assert rel_l2(torch.cat(Cbar, 0).cpu().numpy(), Cb) < GRAD_TOL
+
+
+# ---------------------------------------------------------------------------------------------
+# batched Python entry point (BASELINE config 4's shape) and its CUDA-graph replay
+# ---------------------------------------------------------------------------------------------
+def test_batched_entry_point_cfg4_shape(gu):
+    """256 x (B=64, T=10, 32x32x1): a sample of the problems against the fp64 oracle, and eps = 0.8 by keyword."""
+    from oracle import closed_form as cf
+    s = 1.0 / 15.0
+    P, B, T, H, W, C = 256, 64, 10, 32, 32, 1
+    g = torch.Generator().manual_seed(4)
+    real = torch.rand((P, B, H, T, W, C), generator=g)
+    fake = torch.rand((P, B, H, T, W, C), generator=g)
+    hm = [torch.sigmoid(torch.randn((P, B, T, 8), generator=g)) for _ in range(4)]
+    lv = [t.cuda().requires_grad_(True) for t in (real, fake, *hm)]
+    loss = gu.compute_sinkhorn_loss_batched(lv[0], lv[1], s, *lv[2:])
+    w = torch.linspace(0.5, 1.5, P).cuda()
+    grads = torch.autograd.grad((loss * w).sum(), lv[1:])
+    for q in (0, 117, 255):
+        a = [t[q].numpy().astype(np.float64) for t in (real, fake, *hm)]
+        ref, gref, det = cf.compute_sinkhorn_loss(a[0], a[1], s, 0.8, 100, *a[2:], grad=True)
+        scale = max(abs(det["loss_xy"]), abs(det["loss_xx"]), abs(det["loss_yy"]))
+        assert abs(float(loss[q]) - ref) <= LOSS_TOL * scale, (q, float(loss[q]), ref)
+        for n, gt in zip(GRAD_NAMES[1:], grads):
+            e = rel_l2(gt[q].cpu().numpy().astype(np.float64) / float(w[q]), gref[n])
+            assert e < GRAD_TOL, (q, n, e)
+
+
+def test_batched_graph_replay_many_problems():
+    """Queued CUDA-graph replays of a many-problem chain (150+ problems: the Sinkhorn kernels run in several waves)
+    must keep making progress: with programmatic launches along the chain they hung on B200 / CUDA 12.9; the
+    library therefore uses plain launches above kPdlMaxProblems.  Runs in a child process under a timeout."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "scripts", "batched_graph_probe2.py"), "160", "2", "1", "60"],
+                       capture_output=True, text=True, timeout=180, cwd=root)
+    assert r.returncode == 0 and "60 alternating replays ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
