@@ -52,6 +52,28 @@ def main():
     ms = torch.tensor([e0.elapsed_time(e1) / reps], device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    # stage breakdown (device events around the backend stages of one more evaluation, this rank)
+    be = sm.be
+    stages = {}
+
+    def stage(name, fn):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        out = fn()
+        b.record()
+        torch.cuda.synchronize()
+        stages[name] = a.elapsed_time(b)
+        return out
+    flat = [t[0].reshape(B, -1).contiguous(), t[1].reshape(B, -1).contiguous()] + [x.contiguous() for x in t[2:]]
+    shift = stage("cost_fwd", lambda: be.cost_fwd(*flat))
+    stage("allreduce_shift", lambda: sm._allreduce(shift, dist.ReduceOp.MIN))
+    part = stage("sinkhorn_fwd", lambda: be.sinkhorn_fwd())
+    stage("allreduce_cost", lambda: sm._allreduce(part, dist.ReduceOp.SUM))
+    g3 = torch.tensor([2.0, -1.0, -1.0], device=dev)
+    Cb = stage("sinkhorn_bwd", lambda: be.sinkhorn_bwd(g3))
+    XY = stage("a2a_xy", lambda: sm._columns_of(Cb[0]))
+    YY = stage("a2a_yy", lambda: sm._columns_of(Cb[2]))
+    stage("cost_bwd", lambda: be.cost_bwd(XY, YY))
     # gather the row-sharded gradients
     full = {}
     for k in ("fake", "h_fake", "h_real"):
@@ -82,6 +104,7 @@ def main():
             ok = bool(torch.isfinite(terms).all() and torch.isfinite(full["fake"]).all())
             print(f"world={world} B={B} K={K}: terms {terms.tolist()} (no oracle at this size)", flush=True)
         print(f"fwd+bwd {float(ms):.3f} ms per evaluation (max over ranks)", flush=True)
+        print("stages (ms, rank 0):", {k: round(v, 3) for k, v in stages.items()}, flush=True)
         print("SHARDED_OK" if ok else "SHARDED_FAIL", flush=True)
     if world > 1:
         dist.barrier()
