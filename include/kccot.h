@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define KCCOT_VERSION 100
+#define KCCOT_VERSION 200
 
 /* error codes */
 #define KCCOT_OK 0
@@ -210,17 +210,21 @@ int kccot_pm_bwd(const float* M, int B, int T, int J, float reg_lam, float s, co
 
 /* ------------------------------------------------------------------------------------------
  * Gaussian kernel smoothing — data_utils.py:503-521 (temporal_convolution, mode 1) and
- * :552-582 (gaussian_convolution3D, mode 3).  x, out [B,H,T,W,C].  filt_* are the dense
- * [n,n] REFLECT-pad + 7-tap filter matrices built by the host (row p = output position).
- * out = conv(x) / max(conv(x)); maxval [1] is saved for the backward.
+ * :552-582 (gaussian_convolution3D, mode 3).  x, out [B,H,T,W,C].  out = conv(x) / max(conv(x)) with REFLECT
+ * padding; maxval [1] is saved for the backward.
+ * taps_t / taps_s are HOST arrays of 2*radius+1 normalised weights (gaussian_kernel1d, data_utils.py:483-491);
+ * they travel as kernel arguments: no filter matrix in device memory and no copy when sigma is annealed every
+ * step (:584-586).  Mode 1 filters T with (taps_t, radius_t); mode 3 filters H, T and W with (taps_s, radius_s)
+ * (the reference's 3-D kernel uses the spatial size for all three axes, :553,562-564).  radius 1..6, axes up to
+ * 1024 and longer than the radius.
  * ------------------------------------------------------------------------------------------ */
 size_t kccot_smooth_workspace_bytes(int mode, int B, int H, int T, int W, int C);
-int kccot_smooth_fwd(int mode, const float* x, int B, int H, int T, int W, int C, const float* filt_h,
-                     const float* filt_t, const float* filt_w, float* out, float* maxval, void* ws,
+int kccot_smooth_fwd(int mode, const float* x, int B, int H, int T, int W, int C, const float* taps_t,
+                     int radius_t, const float* taps_s, int radius_s, float* out, float* maxval, void* ws,
                      size_t ws_bytes, void* stream);
 int kccot_smooth_bwd(int mode, const float* gout, const float* out, const float* maxval, int B, int H,
-                     int T, int W, int C, const float* filt_h, const float* filt_t,
-                     const float* filt_w, float* gx, void* ws, size_t ws_bytes, void* stream);
+                     int T, int W, int C, const float* taps_t, int radius_t, const float* taps_s,
+                     int radius_s, float* gx, void* ws, size_t ws_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -61,8 +61,8 @@ SIGNATURES = {
     "kccot_pm_fwd": (_I, [_P, _I, _I, _I, _F, _F, _P, _P, _P]),
     "kccot_pm_bwd": (_I, [_P, _I, _I, _I, _F, _F, _P, _P, _P, _P]),
     "kccot_smooth_workspace_bytes": (_SZ, [_I, _I, _I, _I, _I, _I]),
-    "kccot_smooth_fwd": (_I, [_I, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _SZ, _P]),
-    "kccot_smooth_bwd": (_I, [_I, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _SZ, _P]),
+    "kccot_smooth_fwd": (_I, [_I, _P, _I, _I, _I, _I, _I, _P, _I, _P, _I, _P, _P, _P, _SZ, _P]),
+    "kccot_smooth_bwd": (_I, [_I, _P, _P, _P, _I, _I, _I, _I, _I, _P, _I, _P, _I, _P, _P, _SZ, _P]),
 }
 
 _lib = None
@@ -80,8 +80,8 @@ def load():
             fn = getattr(lib, name)          # AttributeError if the .so does not export a declared symbol
             fn.restype = res
             fn.argtypes = args
-        if lib.kccot_version() != 100:
-            raise OSError(f"{LIB_PATH}: ABI version {lib.kccot_version()} != 100; rebuild")
+        if lib.kccot_version() != 200:
+            raise OSError(f"{LIB_PATH}: ABI version {lib.kccot_version()} != 200; rebuild")
         _lib = lib
     return _lib
 

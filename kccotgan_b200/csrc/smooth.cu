@@ -3,8 +3,11 @@
 // H, T, W (mode 3), then division by the global maximum of the filtered tensor.
 //
 // A pass views the tensor as [outer, n, inner] and applies out[o,p,i] = sum_q A[p,q] in[o,q,i], with A the
-// dense [n,n] matrix of the REFLECT-padded filter built on the host.  A (and its transpose, the adjoint)
-// is banded with radius 3, so every output row needs the 7 rows p-3..p+3 and 7 coefficients coef[p][d].
+// [n,n] matrix of the REFLECT-padded filter: A[p][reflect(p + k - R)] += w[k].  The 2R+1 weights travel as KERNEL
+// ARGUMENTS (no filter matrix in device memory, no host-to-device copy when sigma is annealed every step,
+// data_utils.py:584-586); each kernel derives the band coefficients it needs.  A (and its transpose, the
+// adjoint) is banded with radius R, so every output row needs the rows p-R..p+R and 2R+1 coefficients
+// coef[p][d].  R = 1..6 (kernel sizes 2..13; kernel_train.py:216 uses 6 -> R = 3, the class default 8 -> R = 4).
 // Two kernels, neither with index arithmetic in its inner loop:
 //   axis_col_kernel  (inner >= 64 or n*inner > 1024): one thread per (o, 4 consecutive inner elements) walks
 //                    the n rows with a 7-row register window — every input element is loaded once, 16 bytes
@@ -20,7 +23,23 @@ namespace kccot {
 namespace {
 constexpr int FT = 256;
 constexpr int kTileElems = 8192;     // 32 KB of shared memory per tile
-constexpr int kR = 3, kTaps = 7;
+constexpr int kMaxRadius = 6;
+constexpr int kMaxAxis = 1024;       // coefficient table: n * (2R+1) floats of dynamic shared memory
+
+struct Taps {                        // by value in the kernel parameters
+  float w[2 * kMaxRadius + 1];
+  int r;
+};
+__device__ __forceinline__ int reflect(int q, int n) { return q < 0 ? -q : (q >= n ? 2 * (n - 1) - q : q); }
+// A[p][q] of the REFLECT-padded filter (or its transpose)
+template <int R>
+__device__ __forceinline__ float band_coef(const Taps& tp, int n, int p, int q, bool transposed) {
+  const int row = transposed ? q : p, col = transposed ? p : q;
+  float a = 0.f;
+#pragma unroll
+  for (int k = 0; k < 2 * R + 1; ++k) a += (reflect(row + k - R, n) == col) ? tp.w[k] : 0.f;
+  return a;
+}
 
 __device__ __forceinline__ void atomic_max_float(float* addr, float v) {
   if (v >= 0.f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
@@ -63,15 +82,16 @@ template <> struct Vec<1> {
 
 // MODE bit 0: write `out`; bit 1: reduce the global max into *gmax; bit 2: divide by *divisor;
 // bit 3: apply the BwdIn transform on load; bit 4: use A transposed
-template <int MODE, int V>
+template <int MODE, int V, int R>
 __global__ void __launch_bounds__(FT) axis_col_kernel(const float* __restrict__ in, float* __restrict__ out,
                                                       long long outer, int n, long long inner,
-                                                      const float* __restrict__ A, float* gmax,
+                                                      const Taps tp, float* gmax,
                                                       const float* divisor, BwdIn bw) {
-  __shared__ float coef[64 * kTaps];                       // coef[p][d] = A[p][p + d - 3] (0 outside the matrix)
+  constexpr int kR = R, kTaps = 2 * R + 1;
+  extern __shared__ float coef[];                          // coef[p][d] = A[p][p + d - R] (0 outside the matrix)
   for (int e = threadIdx.x; e < n * kTaps; e += FT) {
     const int p = e / kTaps, q = p + (e % kTaps) - kR;
-    coef[e] = (q >= 0 && q < n) ? ((MODE & 16) ? A[q * n + p] : A[p * n + q]) : 0.f;
+    coef[e] = (q >= 0 && q < n) ? band_coef<R>(tp, n, p, q, (MODE & 16) != 0) : 0.f;
   }
   __syncthreads();
   const long long iv = inner / V;
@@ -122,11 +142,12 @@ __global__ void __launch_bounds__(FT) axis_col_kernel(const float* __restrict__ 
   }
 }
 
-template <int MODE>
+template <int MODE, int R>
 __global__ void __launch_bounds__(1024) axis_tile_kernel(const float* __restrict__ in, float* __restrict__ out,
                                                          long long outer, int n, int inner, int o_chunk,
-                                                         const float* __restrict__ A, float* gmax,
+                                                         const Taps tp, float* gmax,
                                                          const float* divisor, BwdIn bw) {
+  constexpr int kR = R, kTaps = 2 * R + 1;
   extern __shared__ __align__(16) float tile[];            // [o_chunk][n][inner], contiguous like global memory
   const int ni = n * inner;
   const long long o0 = (long long)blockIdx.x * o_chunk;
@@ -166,7 +187,7 @@ __global__ void __launch_bounds__(1024) axis_tile_kernel(const float* __restrict
     for (int d = 0; d < kTaps; ++d) {
       const int q = p + d - kR;
       const bool ok = q >= 0 && q < n;
-      c[d] = ok ? ((MODE & 16) ? A[q * n + p] : A[p * n + q]) : 0.f;
+      c[d] = ok ? band_coef<R>(tp, n, p, q, (MODE & 16) != 0) : 0.f;
       off[d] = ok ? (d - kR) * inner : 0;
     }
   }
@@ -213,29 +234,57 @@ AxisPlan plan_axis(long long outer, int n, long long inner) {
   return p;
 }
 
-template <int MODE>
-int run_axis(const float* in, float* out, const AxisPlan& p, const float* A, int radius, float* gmax,
-             const float* divisor, BwdIn bw, cudaStream_t st) {
-  (void)radius;
+template <int MODE, int R>
+int run_axis_r(const float* in, float* out, const AxisPlan& p, const Taps& tp, float* gmax, const float* divisor,
+               BwdIn bw, cudaStream_t st) {
   if (p.tiled) {
     const int ni = p.n * (int)p.inner;
     const int threads = (ni + 31) / 32 * 32;
     const unsigned grid = (unsigned)((p.outer + p.o_chunk - 1) / p.o_chunk);
     const size_t smem = (size_t)p.o_chunk * ni * sizeof(float);
-    axis_tile_kernel<MODE><<<grid, threads, smem, st>>>(in, out, p.outer, p.n, (int)p.inner, p.o_chunk, A, gmax, divisor, bw);
+    axis_tile_kernel<MODE, R><<<grid, threads, smem, st>>>(in, out, p.outer, p.n, (int)p.inner, p.o_chunk, tp, gmax, divisor, bw);
   } else {
     const bool v4 = (p.inner % 4 == 0) && (reinterpret_cast<uintptr_t>(in) & 15) == 0 &&
                     (!(MODE & 1) || (reinterpret_cast<uintptr_t>(out) & 15) == 0) &&
                     (!(MODE & 8) || (reinterpret_cast<uintptr_t>(bw.out) & 15) == 0);
     const long long total = p.outer * (p.inner / (v4 ? 4 : 1));
     const unsigned grid = (unsigned)((total + FT - 1) / FT);
-    if (v4) axis_col_kernel<MODE, 4><<<grid, FT, 0, st>>>(in, out, p.outer, p.n, p.inner, A, gmax, divisor, bw);
-    else axis_col_kernel<MODE, 1><<<grid, FT, 0, st>>>(in, out, p.outer, p.n, p.inner, A, gmax, divisor, bw);
+    const size_t smem = (size_t)p.n * (2 * R + 1) * sizeof(float);       // <= 1024 * 13 * 4 = 52 KB
+    if (smem > 48 * 1024) {
+      if (v4) KCCOT_CUDA(cudaFuncSetAttribute(axis_col_kernel<MODE, 4, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      else KCCOT_CUDA(cudaFuncSetAttribute(axis_col_kernel<MODE, 1, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    if (v4) axis_col_kernel<MODE, 4, R><<<grid, FT, smem, st>>>(in, out, p.outer, p.n, p.inner, tp, gmax, divisor, bw);
+    else axis_col_kernel<MODE, 1, R><<<grid, FT, smem, st>>>(in, out, p.outer, p.n, p.inner, tp, gmax, divisor, bw);
   }
   KCCOT_LAUNCH_CHECK();
   return KCCOT_OK;
 }
-constexpr int kRadius = 3;    // temporal_kernel_size = spatial_kernel_size = 6 (kernel_train.py:216) -> radius 3
+template <int MODE>
+int run_axis(const float* in, float* out, const AxisPlan& p, const Taps& tp, float* gmax, const float* divisor,
+             BwdIn bw, cudaStream_t st) {
+  switch (tp.r) {
+    case 1: return run_axis_r<MODE, 1>(in, out, p, tp, gmax, divisor, bw, st);
+    case 2: return run_axis_r<MODE, 2>(in, out, p, tp, gmax, divisor, bw, st);
+    case 3: return run_axis_r<MODE, 3>(in, out, p, tp, gmax, divisor, bw, st);
+    case 4: return run_axis_r<MODE, 4>(in, out, p, tp, gmax, divisor, bw, st);
+    case 5: return run_axis_r<MODE, 5>(in, out, p, tp, gmax, divisor, bw, st);
+    case 6: return run_axis_r<MODE, 6>(in, out, p, tp, gmax, divisor, bw, st);
+  }
+  set_error("smoothing radius %d not supported (1..%d)", tp.r, kMaxRadius);
+  return KCCOT_EUNSUPPORTED;
+}
+int make_taps(Taps* tp, const float* w, int radius, const char* what) {
+  KCCOT_CHECK_ARG(w != nullptr, "%s: null weights", what);
+  if (radius < 1 || radius > kMaxRadius) {
+    set_error("%s: smoothing radius %d not supported (kernel sizes 2..%d, radius 1..%d)", what, radius, 2 * kMaxRadius + 1,
+              kMaxRadius);
+    return KCCOT_EUNSUPPORTED;
+  }
+  tp->r = radius;
+  for (int k = 0; k < 2 * kMaxRadius + 1; ++k) tp->w[k] = k < 2 * radius + 1 ? w[k] : 0.f;
+  return KCCOT_OK;
+}
 }  // namespace
 }  // namespace kccot
 
@@ -248,42 +297,51 @@ size_t kccot_smooth_workspace_bytes(int mode, int B, int H, int T, int W, int C)
   return align_up(256 + (mode == 3 ? 2 * align_up(n, 256) : 0), 256);
 }
 
-int kccot_smooth_fwd(int mode, const float* x, int B, int H, int T, int W, int C, const float* filt_h,
-                     const float* filt_t, const float* filt_w, float* out, float* maxval, void* ws, size_t ws_bytes,
-                     void* stream) {
+int kccot_smooth_fwd(int mode, const float* x, int B, int H, int T, int W, int C, const float* taps_t, int radius_t,
+                     const float* taps_s, int radius_s, float* out, float* maxval, void* ws, size_t ws_bytes, void* stream) {
   KCCOT_CHECK_ARG(mode == 1 || mode == 3, "smoothing mode must be 1 (temporal) or 3 (3-D); the reference's '2d' "
                                           "branch raises (data_utils.py:537-538)");
-  KCCOT_CHECK_ARG(x && out && maxval && filt_t, "null pointer");
-  KCCOT_CHECK_ARG(B >= 1 && H >= 1 && W >= 1 && C >= 1 && T > kRadius, "REFLECT padding needs T > 3 (T=%d)", T);
-  KCCOT_CHECK_ARG(T <= 64 && H <= 64 && W <= 64, "axis longer than 64 not supported (H=%d T=%d W=%d)", H, T, W);
+  KCCOT_CHECK_ARG(x && out && maxval, "null pointer");
+  KCCOT_CHECK_ARG(B >= 1 && H >= 1 && T >= 1 && W >= 1 && C >= 1, "bad sizes");
+  KCCOT_CHECK_ARG(T <= kMaxAxis && H <= kMaxAxis && W <= kMaxAxis, "axis longer than %d not supported (H=%d T=%d W=%d)", kMaxAxis,
+                  H, T, W);
   cudaStream_t st = (cudaStream_t)stream;
+  Taps tp;
+  if (int rc = mode == 1 ? make_taps(&tp, taps_t, radius_t, "temporal_convolution") : make_taps(&tp, taps_s, radius_s,
+                                                                                             "gaussian_convolution3D"))
+    return rc;
+  KCCOT_CHECK_ARG(T > tp.r, "REFLECT padding by %d needs T > %d (T=%d)", tp.r, tp.r, T);
   init_max_kernel<<<1, 1, 0, st>>>(maxval);
   KCCOT_LAUNCH_CHECK();
   const AxisPlan pt = plan_axis((long long)B * H, T, (long long)W * C);
   BwdIn none{};
   if (mode == 1) {
-    if (int rc = run_axis<2>(x, nullptr, pt, filt_t, kRadius, maxval, nullptr, none, st)) return rc;
-    return run_axis<1 | 4>(x, out, pt, filt_t, kRadius, nullptr, maxval, none, st);
+    if (int rc = run_axis<2>(x, nullptr, pt, tp, maxval, nullptr, none, st)) return rc;
+    return run_axis<1 | 4>(x, out, pt, tp, nullptr, maxval, none, st);
   }
-  KCCOT_CHECK_ARG(filt_h && filt_w && H > kRadius && W > kRadius, "3-D smoothing needs H, W > 3 and all three filters");
+  KCCOT_CHECK_ARG(H > tp.r && W > tp.r, "3-D smoothing needs H, W > %d (H=%d W=%d)", tp.r, H, W);
   const size_t n = align_up((size_t)B * H * T * W * C * sizeof(float), 256);
   KCCOT_CHECK_ARG(ws && ws_bytes >= 256 + 2 * n, "workspace too small");
   float* t1 = (float*)((char*)ws + 256);
   float* t2 = (float*)((char*)ws + 256 + n);
   const AxisPlan ph = plan_axis(B, H, (long long)T * W * C);
   const AxisPlan pw = plan_axis((long long)B * H * T, W, C);
-  if (int rc = run_axis<1>(x, t1, ph, filt_h, kRadius, nullptr, nullptr, none, st)) return rc;
-  if (int rc = run_axis<1>(t1, t2, pt, filt_t, kRadius, nullptr, nullptr, none, st)) return rc;
-  if (int rc = run_axis<2>(t2, nullptr, pw, filt_w, kRadius, maxval, nullptr, none, st)) return rc;
-  return run_axis<1 | 4>(t2, out, pw, filt_w, kRadius, nullptr, maxval, none, st);
+  if (int rc = run_axis<1>(x, t1, ph, tp, nullptr, nullptr, none, st)) return rc;
+  if (int rc = run_axis<1>(t1, t2, pt, tp, nullptr, nullptr, none, st)) return rc;
+  if (int rc = run_axis<2>(t2, nullptr, pw, tp, maxval, nullptr, none, st)) return rc;
+  return run_axis<1 | 4>(t2, out, pw, tp, nullptr, maxval, none, st);
 }
 
 int kccot_smooth_bwd(int mode, const float* gout, const float* out, const float* maxval, int B, int H, int T, int W,
-                     int C, const float* filt_h, const float* filt_t, const float* filt_w, float* gx, void* ws,
+                     int C, const float* taps_t, int radius_t, const float* taps_s, int radius_s, float* gx, void* ws,
                      size_t ws_bytes, void* stream) {
   KCCOT_CHECK_ARG(mode == 1 || mode == 3, "smoothing mode must be 1 or 3");
-  KCCOT_CHECK_ARG(gout && out && maxval && gx && filt_t && ws && ws_bytes >= 256, "null pointer / workspace");
+  KCCOT_CHECK_ARG(gout && out && maxval && gx && ws && ws_bytes >= 256, "null pointer / workspace");
   cudaStream_t st = (cudaStream_t)stream;
+  Taps tp;
+  if (int rc = mode == 1 ? make_taps(&tp, taps_t, radius_t, "temporal_convolution") : make_taps(&tp, taps_s, radius_s,
+                                                                                             "gaussian_convolution3D"))
+    return rc;
   const long long nel = (long long)B * H * T * W * C;
   float* sums = (float*)ws;
   KCCOT_CUDA(cudaMemsetAsync(sums, 0, 2 * sizeof(float), st));
@@ -292,16 +350,16 @@ int kccot_smooth_bwd(int mode, const float* gout, const float* out, const float*
   BwdIn bw{out, maxval, sums};
   BwdIn none{};
   const AxisPlan pt = plan_axis((long long)B * H, T, (long long)W * C);
-  if (mode == 1) return run_axis<1 | 8 | 16>(gout, gx, pt, filt_t, kRadius, nullptr, nullptr, bw, st);
+  if (mode == 1) return run_axis<1 | 8 | 16>(gout, gx, pt, tp, nullptr, nullptr, bw, st);
   const size_t n = align_up((size_t)nel * sizeof(float), 256);
-  KCCOT_CHECK_ARG(filt_h && filt_w && ws_bytes >= 256 + 2 * n, "workspace too small");
+  KCCOT_CHECK_ARG(ws_bytes >= 256 + 2 * n, "workspace too small");
   float* t1 = (float*)((char*)ws + 256);
   float* t2 = (float*)((char*)ws + 256 + n);
   const AxisPlan ph = plan_axis(B, H, (long long)T * W * C);
   const AxisPlan pw = plan_axis((long long)B * H * T, W, C);
-  if (int rc = run_axis<1 | 8 | 16>(gout, t1, pw, filt_w, kRadius, nullptr, nullptr, bw, st)) return rc;
-  if (int rc = run_axis<1 | 16>(t1, t2, pt, filt_t, kRadius, nullptr, nullptr, none, st)) return rc;
-  return run_axis<1 | 16>(t2, gx, ph, filt_h, kRadius, nullptr, nullptr, none, st);
+  if (int rc = run_axis<1 | 8 | 16>(gout, t1, pw, tp, nullptr, nullptr, bw, st)) return rc;
+  if (int rc = run_axis<1 | 16>(t1, t2, pt, tp, nullptr, nullptr, none, st)) return rc;
+  return run_axis<1 | 16>(t2, gx, ph, tp, nullptr, nullptr, none, st);
 }
 
 }  // extern "C"

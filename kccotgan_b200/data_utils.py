@@ -16,7 +16,6 @@ class KernelSmoothing:
         # data_utils.py:479-481
         self.temporal_radius = temporal_kernel_size // 2
         self.spatial_radius = spatial_kernel_size // 2
-        self._filters = {}
 
     # -- weights --------------------------------------------------------------------------------
     @staticmethod
@@ -40,34 +39,17 @@ class KernelSmoothing:
         k = (k / k.sum(dtype=np.float32)).astype(np.float32)
         return torch.from_numpy(k[:, :, :, None, None]).to(device)
 
-    def _filter_matrix(self, n, radius, sigma, device):
-        """Dense [n,n] matrix of REFLECT pad (data_utils.py:513) + VALID cross-correlation (:515)."""
-        key = (n, radius, float(sigma), str(device))
-        if key not in self._filters:
-            if n <= radius:
-                raise ValueError(f"REFLECT padding by {radius} needs an axis longer than {radius}, got {n}")
-            if radius != 3:
-                raise ValueError("libkccot's smoothing kernels are built for kernel size 6 (radius 3), the value "
-                                 "kernel_train.py:216 uses")
-            w = self._weights(radius, sigma)
-            A = np.zeros((n, n), dtype=np.float32)
-            for p in range(n):
-                for k in range(2 * radius + 1):
-                    q = p + k - radius
-                    q = -q if q < 0 else q
-                    q = 2 * (n - 1) - q if q >= n else q
-                    A[p, q] += w[k]
-            if len(self._filters) > 64:
-                self._filters.clear()
-            self._filters[key] = torch.from_numpy(A).to(device)
-        return self._filters[key]
-
     # -- convolutions ---------------------------------------------------------------------------
+    @staticmethod
+    def _check_axis(name, n, radius):
+        if n <= radius:
+            raise ValueError(f"REFLECT padding by {radius} needs the {name} axis longer than {radius}, got {n}")
+
     def temporal_convolution(self, inputs, sigma):
-        """data_utils.py:503-521 — 7-tap REFLECT filter along T, / global max."""
+        """data_utils.py:503-521 — (2r+1)-tap REFLECT filter along T, / global max."""
         inputs = _check(inputs, "inputs", 5)
-        ft = self._filter_matrix(inputs.shape[2], self.temporal_radius, sigma, inputs.device)
-        return SmoothFn.apply(inputs, 1, None, ft, None)
+        self._check_axis("T", inputs.shape[2], self.temporal_radius)
+        return SmoothFn.apply(inputs, 1, tuple(self._weights(self.temporal_radius, sigma)), None)
 
     def spatial_convolution(self, inputs, sigma):
         """data_utils.py:523-550 — BROKEN in the reference: the VALID conv2d shrinks H, W by 2r and the
@@ -79,13 +61,13 @@ class KernelSmoothing:
                          "(the reference's '2d' kernel raises here, data_utils.py:537-538)")
 
     def gaussian_convolution3D(self, inputs, sigma):
-        """data_utils.py:552-582 — 7^3 REFLECT filter over (H,T,W) per channel (three separable
-        7-tap passes), / global max.  Uses the SPATIAL radius for all three axes (:553,562-564)."""
+        """data_utils.py:552-582 — (2r+1)^3 REFLECT filter over (H,T,W) per channel (three separable
+        passes), / global max.  Uses the SPATIAL radius for all three axes (:553,562-564)."""
         inputs = _check(inputs, "inputs", 5)
         _, H, T, W, _ = inputs.shape
-        r, dev = self.spatial_radius, inputs.device
-        return SmoothFn.apply(inputs, 3, self._filter_matrix(H, r, sigma, dev), self._filter_matrix(T, r, sigma, dev),
-                              self._filter_matrix(W, r, sigma, dev))
+        for name, n in (("H", H), ("T", T), ("W", W)):
+            self._check_axis(name, n, self.spatial_radius)
+        return SmoothFn.apply(inputs, 3, None, tuple(self._weights(self.spatial_radius, sigma)))
 
     def annealing_sigma(self, init_sigma, step, decay_steps=500, decay_rate=0.975):
         """data_utils.py:584-586."""

@@ -350,33 +350,46 @@ class MartingalePenaltyFn(torch.autograd.Function):
 # ------------------------------------------------------------------------------------------------
 # Gaussian smoothing
 # ------------------------------------------------------------------------------------------------
+def _taps(w):
+    """Host weights -> (ctypes float array, radius); None -> (None, 0)."""
+    if w is None:
+        return None, 0
+    arr = (ctypes.c_float * len(w))(*[float(v) for v in w])
+    return arr, (len(w) - 1) // 2
+
+
 class SmoothFn(torch.autograd.Function):
+    """mode 1: `taps_t` filters T; mode 3: `taps_s` filters H, T and W.  The weights are host sequences (they become
+    kernel arguments: nothing is copied to the device, so an annealed sigma costs nothing per step)."""
+
     @staticmethod
-    def forward(ctx, x, mode, filt_h, filt_t, filt_w):
+    def forward(ctx, x, mode, taps_t, taps_s):
         x = _check(x, "inputs", 5)
         B, H, T, W, C = x.shape
         dev = x.device
         out = torch.empty_like(x)
         maxval = torch.empty((1,), dtype=torch.float32, device=dev)
         ws = _ws(_lib.load().kccot_smooth_workspace_bytes(mode, B, H, T, W, C), dev)
+        at, rt = _taps(taps_t)
+        as_, rs = _taps(taps_s)
         with torch.cuda.device(dev):
-            _lib.call("kccot_smooth_fwd", mode, _ptr(x), B, H, T, W, C, _ptr(filt_h), _ptr(filt_t), _ptr(filt_w),
-                      _ptr(out), _ptr(maxval), _ptr(ws), ws.numel(), _stream(dev))
-        ctx.save_for_backward(out, maxval, filt_t, *([filt_h, filt_w] if mode == 3 else []))
-        ctx.mode = mode
+            _lib.call("kccot_smooth_fwd", mode, _ptr(x), B, H, T, W, C, at, rt, as_, rs, _ptr(out), _ptr(maxval), _ptr(ws),
+                      ws.numel(), _stream(dev))
+        ctx.save_for_backward(out, maxval)
+        ctx.mode, ctx.taps = mode, (taps_t, taps_s)
         return out
 
     @staticmethod
     def backward(ctx, gout):
-        saved = ctx.saved_tensors
-        out, maxval, filt_t = saved[0], saved[1], saved[2]
-        filt_h, filt_w = (saved[3], saved[4]) if ctx.mode == 3 else (None, None)
+        out, maxval = ctx.saved_tensors
         B, H, T, W, C = out.shape
         dev = out.device
         gout = gout.contiguous().float()
         gx = torch.empty_like(out)
         ws = _ws(_lib.load().kccot_smooth_workspace_bytes(ctx.mode, B, H, T, W, C), dev)
+        at, rt = _taps(ctx.taps[0])
+        as_, rs = _taps(ctx.taps[1])
         with torch.cuda.device(dev):
-            _lib.call("kccot_smooth_bwd", ctx.mode, _ptr(gout), _ptr(out), _ptr(maxval), B, H, T, W, C, _ptr(filt_h),
-                      _ptr(filt_t), _ptr(filt_w), _ptr(gx), _ptr(ws), ws.numel(), _stream(dev))
-        return gx, None, None, None, None
+            _lib.call("kccot_smooth_bwd", ctx.mode, _ptr(gout), _ptr(out), _ptr(maxval), B, H, T, W, C, at, rt, as_, rs,
+                      _ptr(gx), _ptr(ws), ws.numel(), _stream(dev))
+        return gx, None, None, None

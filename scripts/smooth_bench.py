@@ -29,18 +29,16 @@ for name, op in (("temporal_convolution", ks.temporal_convolution), ("gaussian_c
     lib = _lib.load()
     mode = 1 if name == "temporal_convolution" else 3
     dev = xs[0].device
-    ft = ks._filter_matrix(T, 3, 5.0, dev)
-    fh = ks._filter_matrix(H, 3, 5.0, dev) if mode == 3 else None
-    fw = ks._filter_matrix(W, 3, 5.0, dev) if mode == 3 else None
+    taps, rad = F._taps(tuple(ks._weights(3, 5.0)))
     x0 = xs[0].detach(); g0 = gs[0]
     o0 = torch.empty_like(x0); gx0 = torch.empty_like(x0); mx = torch.empty(1, device=dev)
     wsb = torch.empty(lib.kccot_smooth_workspace_bytes(mode, B, H, T, W, C), dtype=torch.uint8, device=dev)
     p = F._ptr
     def fwd_abi():
-        _lib.call("kccot_smooth_fwd", mode, p(x0), B, H, T, W, C, p(fh), p(ft), p(fw), p(o0), p(mx), p(wsb), wsb.numel(),
+        _lib.call("kccot_smooth_fwd", mode, p(x0), B, H, T, W, C, taps, rad, taps, rad, p(o0), p(mx), p(wsb), wsb.numel(),
                   F._stream(dev))
     def bwd_abi():
-        _lib.call("kccot_smooth_bwd", mode, p(g0), p(o0), p(mx), B, H, T, W, C, p(fh), p(ft), p(fw), p(gx0), p(wsb),
+        _lib.call("kccot_smooth_bwd", mode, p(g0), p(o0), p(mx), B, H, T, W, C, taps, rad, taps, rad, p(gx0), p(wsb),
                   wsb.numel(), F._stream(dev))
     fwd_abi(); bwd_abi(); torch.cuda.synchronize()
     gf, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()

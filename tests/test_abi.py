@@ -29,7 +29,7 @@ def test_header_symbols_exported(lib):
 
 def test_version_and_no_cpu_fallback(lib):
     from kccotgan_b200 import _lib
-    assert lib.kccot_version() == 100
+    assert lib.kccot_version() == 200
     if not torch.cuda.is_available():
         assert lib.kccot_device_check() != 0
         assert "no CUDA device" in _lib.last_error()
@@ -49,7 +49,7 @@ def test_argument_errors_are_value_errors(lib):
     with pytest.raises(ValueError):
         _lib.call("kccot_cost_fwd", None, None, 1, 8, 8, 64, None, None, None, None, 0, 0, 0.1, None, None, 0, 0, None)
     with pytest.raises(ValueError):
-        _lib.call("kccot_smooth_fwd", 2, None, 1, 8, 8, 8, 1, None, None, None, None, None, None, 0, None)
+        _lib.call("kccot_smooth_fwd", 2, None, 1, 8, 8, 8, 1, None, 3, None, 3, None, None, None, 0, None)
     assert "2d" in _lib.last_error()
 
 
@@ -94,17 +94,20 @@ def test_product_does_not_import_oracle():
             assert "oracle." not in src and "/oracle" not in src, fn
 
 
-def test_filter_matrix_matches_oracle():
+def test_smoothing_weights_match_oracle():
+    """The host side only produces the 2r+1 weights (the REFLECT band is formed inside the kernels): same numbers
+    as the reference's gaussian_kernel1d for every radius the library takes, default constructor included."""
     import numpy as np
     from kccotgan_b200.data_utils import KernelSmoothing
     from oracle import closed_form as cf
-    ks = KernelSmoothing(6, 6)
-    for n in (4, 7, 12, 64):
-        A = ks._filter_matrix(n, 3, 5.0, "cpu").numpy()
-        assert np.allclose(A, cf._filter_matrix(n, 3, 5.0), atol=1e-7)
-        assert np.allclose(A.sum(axis=1), 1.0, atol=1e-6)
-    with pytest.raises(ValueError):
-        ks._filter_matrix(3, 3, 5.0, "cpu")
+    ks = KernelSmoothing()                       # reference defaults: temporal 6 -> radius 3, spatial 8 -> radius 4
+    assert (ks.temporal_radius, ks.spatial_radius) == (3, 4)
+    for r in range(1, 7):
+        for sigma in (0.7, 1.7, 5.0):
+            w = ks._weights(r, sigma)
+            assert w.shape == (2 * r + 1,) and w.dtype == np.float32
+            assert np.allclose(w, cf.gaussian_kernel1d(r, sigma), atol=1e-7)
+            assert abs(float(w.sum()) - 1.0) < 1e-6
 
 
 def test_header_is_plain_c(tmp_path):

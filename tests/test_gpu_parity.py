@@ -421,6 +421,55 @@ def test_smoothing_shapes(shape):
         assert rel_l2(gx.cpu().numpy(), rg) < GRAD_TOL, (mode, shape)
 
 
+@pytest.mark.parametrize("tk,sk,shape", [
+    (8, 8, (2, 12, 10, 12, 3)),       # the class's own default spatial size 8 -> radius 4 (raised)
+    (6, 8, (2, 16, 7, 16, 1)),        # KernelSmoothing() defaults: temporal radius 3, spatial radius 4
+    (2, 3, (3, 6, 5, 6, 2)),          # radius 1
+    (12, 12, (1, 16, 14, 16, 1)),     # radius 6
+    (6, 6, (1, 96, 8, 80, 1)),        # axes longer than 64
+    (6, 6, (1, 8, 200, 4, 1)),        # a long temporal axis
+])
+def test_smoothing_radius_and_axis_range(tk, sk, shape):
+    from kccotgan_b200.data_utils import KernelSmoothing
+    from oracle import closed_form as cf
+    ks = KernelSmoothing(temporal_kernel_size=tk, spatial_kernel_size=sk)
+    g = torch.Generator().manual_seed(tk * 100 + sk)
+    x = torch.rand(shape, generator=g)
+    go = torch.randn(shape, generator=g)
+    for mode, fn, cfn, r in (("1d", ks.temporal_convolution, cf.temporal_convolution, tk // 2),
+                             ("3d", ks.gaussian_convolution3D, cf.gaussian_convolution3D, sk // 2)):
+        xl = x.cuda().requires_grad_(True)
+        out = fn(xl, 2.0)
+        gx, = torch.autograd.grad(out, xl, go.cuda())
+        ro, rg = cfn(x.numpy(), 2.0, radius=r, grad_out=go.numpy())
+        assert float(out.max()) == 1.0
+        assert rel_l2(out.detach().cpu().numpy(), ro) < 1e-5, (mode, shape)
+        assert rel_l2(gx.cpu().numpy(), rg) < GRAD_TOL, (mode, shape)
+    with pytest.raises((ValueError, RuntimeError)):
+        KernelSmoothing(30, 30).temporal_convolution(torch.rand(1, 4, 40, 4, 1, device="cuda"), 2.0)     # radius 15
+
+
+def test_smoothing_annealed_sigma_is_graph_capturable():
+    """The filter weights are kernel arguments: a smoothing call with a never-seen sigma copies nothing to the
+    device, so it can sit inside a CUDA-graph capture (the dense filter matrix was rebuilt on the host
+    and copied from pageable memory for every new sigma)."""
+    from kccotgan_b200.data_utils import KernelSmoothing
+    from oracle import closed_form as cf
+    ks = KernelSmoothing(6, 6)
+    x = torch.rand(2, 8, 6, 8, 1)
+    xd = x.cuda()
+    sig = ks.annealing_sigma(5.0, 12345)
+    ks.temporal_convolution(xd, 4.0)                     # warm-up with a different sigma
+    torch.cuda.synchronize()
+    gr = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(gr):
+        out = ks.temporal_convolution(xd, sig)
+    gr.replay()
+    torch.cuda.synchronize()
+    ro = cf.temporal_convolution(x.numpy(), sig)
+    assert rel_l2(out.cpu().numpy(), ro) < 1e-5
+
+
 @pytest.mark.parametrize("kernel", ["none", "1d", "3d"])
 def test_training_step_closures(kernel):
     """kernel_train.py:219-292 with stub networks (kccotgan_b200.train_step): the loss the generator step
