@@ -7,7 +7,6 @@
 namespace kccot {
 static thread_local char g_err[512] = "";
 std::atomic<unsigned long long> g_launches{0};
-thread_local bool t_pdl_ok = true;
 
 void set_error(const char* fmt, ...) {
   va_list ap;

@@ -32,9 +32,27 @@ inline void count_launch(int n = 1) { g_launches.fetch_add((unsigned long long)n
     }                                                                                     \
   } while (0)
 
+#ifdef KCCOT_DEV
+// development build: KCCOT_SYNC_EACH=1 synchronises after every launch and logs its source line (finds the kernel
+// that does not come back)
+inline void dev_sync_each(const char* file, int line) {
+  static const bool on = getenv("KCCOT_SYNC_EACH") != nullptr;
+  if (!on) return;
+  fprintf(stderr, "[kccot] launched %s:%d ...", file, line);
+  fflush(stderr);
+  cudaError_t e = cudaDeviceSynchronize();
+  fprintf(stderr, " done (%s)\n", cudaGetErrorString(e));
+  fflush(stderr);
+}
+#define KCCOT_DEV_SYNC() ::kccot::dev_sync_each(__FILE__, __LINE__)
+#else
+#define KCCOT_DEV_SYNC() do { } while (0)
+#endif
+
 #define KCCOT_LAUNCH_CHECK()                                                             \
   do {                                                                                   \
     ::kccot::count_launch();                                                             \
+    KCCOT_DEV_SYNC();                                                                    \
     cudaError_t _e = cudaGetLastError();                                                 \
     if (_e != cudaSuccess) {                                                             \
       ::kccot::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e),      \
@@ -65,19 +83,6 @@ inline bool smem_attr_needed(size_t (&cache)[kMaxDevices], size_t want) {
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
-// Programmatic launches are used only for the latency-bound chains of a FEW problems.  With hundreds of problems per
-// call the Sinkhorn kernels run in several waves, nothing is gained from overlapping prologues, and on B200 /
-// CUDA 12.9 queued CUDA-graph replays of such a chain stopped making progress (nprob >= 150 hung, nprob <= 64 ran;
-// the same graphs without the launch attribute ran).  The C-ABI entry points open a PdlScope with their problem
-// count; launch_pdl() degrades to a plain launch outside the limit.
-constexpr int kPdlMaxProblems = 16;
-extern thread_local bool t_pdl_ok;
-struct PdlScope {
-  bool prev;
-  explicit PdlScope(bool ok) : prev(t_pdl_ok) { t_pdl_ok = t_pdl_ok && ok; }
-  ~PdlScope() { t_pdl_ok = prev; }
-};
-
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
                               Args... args) {
@@ -90,7 +95,7 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = t_pdl_ok ? 1 : 0;
+  cfg.numAttrs = 1;
 #ifdef KCCOT_DEV
   static const bool no_pdl = getenv("KCCOT_NO_PDL") != nullptr;      // development build: A/B switch
   if (no_pdl) cfg.numAttrs = 0;

@@ -57,7 +57,6 @@ int kccot_cost_fwd(const float* x, const float* y, int nprob, int Bx, int By, lo
                    const float* M1, const float* h2, const float* M2, int T, int J, float s, float* C, void* ws,
                    size_t ws_bytes, int flags, void* stream) {
   if (int rc = check_common(nprob, Bx, By, K)) return rc;
-  PdlScope pdl(nprob <= kPdlMaxProblems);
   KCCOT_CHECK_ARG(x && y && C && ws, "null pointer");
   KCCOT_CHECK_ARG((h1 == nullptr) == (M1 == nullptr) && (h2 == nullptr) == (M2 == nullptr),
                   "h and M must be given in pairs");
@@ -133,7 +132,6 @@ int mixed_cost_fwd_impl(const float* real, const float* fake, int nprob, int B, 
                         const float* m_real, const float* h_real, const float* m_fake, int T, int J, float s,
                         float* C3, void* ws, size_t ws_bytes, int flags, void* stream, int* zero_counters) {
   if (int rc = check_common(nprob, B, B, K)) return rc;
-  PdlScope pdl(nprob <= kPdlMaxProblems);
   KCCOT_CHECK_ARG(real && fake && h_fake && m_real && h_real && m_fake && C3 && ws, "null pointer");
   KCCOT_CHECK_ARG(T >= 2 && J >= 1, "martingale term needs T >= 2, J >= 1 (T=%d J=%d)", T, J);
   cudaStream_t st = (cudaStream_t)stream;
@@ -236,7 +234,6 @@ size_t kccot_cost_bwd_workspace_bytes(int nprob, int Bx, int By, long long K) {
 int kccot_cost_bwd(const float* Cbar, const float* x, const float* y, int nprob, int Bx, int By, long long K, float s,
                    float* gx, float* gy, void* ws, size_t ws_bytes, int flags, void* stream) {
   if (int rc = check_common(nprob, Bx, By, K)) return rc;
-  PdlScope pdl(nprob <= kPdlMaxProblems);
   KCCOT_CHECK_ARG(Cbar && x && y, "null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   const int acc = (flags & KCCOT_FLAG_ACCUMULATE) ? 1 : 0;
@@ -285,7 +282,6 @@ int kccot_mixed_cost_bwd(const float* Cbar3, const float* real, const float* fak
                          int J, float s, float* g_real, float* g_fake, float* gh_fake, float* gm_real, float* gh_real,
                          float* gm_fake, void* ws, size_t ws_bytes, int flags, void* stream) {
   if (int rc = check_common(nprob, B, B, K)) return rc;
-  PdlScope pdl(nprob <= kPdlMaxProblems);
   KCCOT_CHECK_ARG(Cbar3 && real && fake && h_fake && m_real && h_real && m_fake, "null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   const int acc = (flags & KCCOT_FLAG_ACCUMULATE) ? 1 : 0;

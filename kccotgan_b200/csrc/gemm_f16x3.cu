@@ -174,6 +174,11 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
+      // drain the asynchronous tcgen05.commit arrivals on empty[] before the CTA may exit (see grad_tcgen05.cu)
+      for (int i = 0; i < kStages; ++i) {
+        tc::mbar_wait(&bars.empty[stage], phase ^ 1);
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
     }
   } else if (warp == 1) {
     // ------------------------------- MMA issuer -----------------------------------------------

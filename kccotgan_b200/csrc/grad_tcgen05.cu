@@ -33,11 +33,11 @@ namespace {
 constexpr int kCols = 32;                  // video columns per work tile (UMMA N) = one TMA box
 constexpr int kBoxCols = 32;               // fp32 columns per TMA box (128-byte swizzle row)
 constexpr int kMaxN = 64;                  // output rows per launch
-constexpr int kConvWarps = 8;
+constexpr int kMaxStages = 9;               // 162 KB: leaves room for a martingale CTA (44 KB) on the same SM; 12 measured no faster
+constexpr int kConvWarps = kMaxStages;      // ONE converter warp per ring slot (see the converter branch for why)
 constexpr int kConvThreads = kConvWarps * 32;
 constexpr int kEpiWarps = 4;
-constexpr int kThreads = 64 + kConvThreads + kEpiWarps * 32;   // 320
-constexpr int kMaxStages = 9;               // 162 KB: leaves room for a martingale CTA (44 KB) on the same SM; 12 measured no faster
+constexpr int kThreads = 64 + kConvThreads + kEpiWarps * 32;   // 480
 constexpr int kAccBufs = 4;
 constexpr int kAccCols = 64;               // per tile: [W.Zhi | W.Zlo], 32 columns each
 constexpr int kTmemCols = 512;             // W'hi [0,128) | W'lo [128,256) | 4 accumulator buffers x 64 columns
@@ -261,6 +261,12 @@ grad_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ 
           if (++stage == nstages) { stage = 0; phase ^= 1; }
         }
       }
+      // Drain: the tcgen05.commit arrivals on empty[] are asynchronous and nobody else waits for the last ones; an
+      // arrival must not land after the CTA has exited (the shared memory then belongs to the next CTA on this SM).
+      for (int i = 0; i < nstages; ++i) {
+        tc::mbar_wait(&bars.empty[stage], phase ^ 1);
+        if (++stage == nstages) { stage = 0; phase ^= 1; }
+      }
     }
   } else if (warp == 1) {
     // ------------------------------- MMA issuer -----------------------------------------------
@@ -309,46 +315,50 @@ grad_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ 
     }
   } else if (warp < 2 + kConvWarps) {
     // ------------------------------- tf32 hi / lo split ---------------------------------------
-    // Warp-per-stage: converter warp cw owns every kConvWarps-th box, so up to 8 boxes are being
-    // converted at once (all warps on one box serialised the boxes at ~600 cycles each).
+    // Warp-per-SLOT: converter warp cw owns ring slot cw, i.e. the boxes cw, cw + nstages, ... — up to nstages boxes
+    // are being converted at once (all warps on one box serialised the boxes at ~600 cycles each).
+    // The owner sees EVERY phase of full[cw] in order, which the parity wait needs.  An earlier version dealt the
+    // boxes round-robin over 8 warps with 9 slots: after box n a warp went on to box n + 8, which lives in the slot of
+    // box n - 1, a box that ANOTHER warp waits for.  TMA loads complete out of order; when box n landed and was
+    // converted before box n - 1 had landed, full[slot(n-1)] still showed the phase before box n - 1, whose parity is
+    // the one box n + 8 waits for: the wait passed, the warp converted a slot that was being filled and arrived on
+    // conv[] a pass early, and the barriers of the ring went out of step for good (the kernel hung about once in a
+    // few hundred thousand CTAs, found with the development build's bounded waits).
     const int cw = warp - 2;
-    long long n = 0;                                          // running stage number
-    for (long long t = t_begin; t < t_end; ++t) {
-      for (int half = 0; half < 2; ++half) {
+    if (cw < nstages) {
+      const int nhalves = (Bx ? 1 : 0) + (By ? 1 : 0);
+      const long long nbox = (t_end - t_begin) * nhalves;
+      const uint32_t hi = tc::smem_u32(st_hi + (size_t)cw * stage_bytes);
+      const uint32_t lo = tc::smem_u32(st_lo + (size_t)cw * stage_bytes);
+      int phase = 0;
+      for (long long n = cw; n < nbox; n += nstages, phase ^= 1) {
+        const int half = nhalves == 2 ? (int)(n & 1) : (Bx ? 0 : 1);
         const int rows = half ? By : Bx;
-        if (rows == 0) continue;
-        if ((int)(n % kConvWarps) == cw) {
-          const int stage = (int)(n % nstages);
-          const int phase = (int)((n / nstages) & 1);
-          tc::mbar_wait(&bars.full[stage], phase);
-          if (cw == 0 && lane == 0) KTRACE(2, 0);
-          const uint32_t hi = tc::smem_u32(st_hi + (size_t)stage * stage_bytes);
-          const uint32_t lo = tc::smem_u32(st_lo + (size_t)stage * stage_bytes);
-          const int n16 = rows * 8;                           // 16-byte units in this box (multiple of 64)
-          for (int e0 = lane; e0 < n16; e0 += 32 * 4) {
-            float4 v[4];
+        tc::mbar_wait(&bars.full[cw], phase);
+        if (cw == 0 && lane == 0) KTRACE(2, 0);
+        const int n16 = rows * 8;                           // 16-byte units in this box (multiple of 64)
+        for (int e0 = lane; e0 < n16; e0 += 32 * 4) {
+          float4 v[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
-              if (e0 + 32 * u < n16) v[u] = tc::lds128(hi + (e0 + 32 * u) * 16);
+          for (int u = 0; u < 4; ++u)
+            if (e0 + 32 * u < n16) v[u] = tc::lds128(hi + (e0 + 32 * u) * 16);
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const int e = e0 + 32 * u;
-              if (e < n16) {
-                float4 h, l;
-                h.x = tc::to_tf32(v[u].x); h.y = tc::to_tf32(v[u].y); h.z = tc::to_tf32(v[u].z); h.w = tc::to_tf32(v[u].w);
-                l.x = tc::to_tf32(v[u].x - h.x); l.y = tc::to_tf32(v[u].y - h.y);
-                l.z = tc::to_tf32(v[u].z - h.z); l.w = tc::to_tf32(v[u].w - h.w);
-                tc::sts128(hi + e * 16, h);
-                tc::sts128(lo + e * 16, l);
-              }
+          for (int u = 0; u < 4; ++u) {
+            const int e = e0 + 32 * u;
+            if (e < n16) {
+              float4 h, l;
+              h.x = tc::to_tf32(v[u].x); h.y = tc::to_tf32(v[u].y); h.z = tc::to_tf32(v[u].z); h.w = tc::to_tf32(v[u].w);
+              l.x = tc::to_tf32(v[u].x - h.x); l.y = tc::to_tf32(v[u].y - h.y);
+              l.z = tc::to_tf32(v[u].z - h.z); l.w = tc::to_tf32(v[u].w - h.w);
+              tc::sts128(hi + e * 16, h);
+              tc::sts128(lo + e * 16, l);
             }
           }
-          tc::fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) tc::mbar_arrive(&bars.conv[stage]);
-          if (cw == 0 && lane == 0) { KTRACE(2, 1); ++trn; }
         }
-        ++n;
+        tc::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&bars.conv[cw]);
+        if (cw == 0 && lane == 0) { KTRACE(2, 1); ++trn; }
       }
     }
   } else {
@@ -518,4 +528,8 @@ int launch_grad_pair_tc(const float* Cbar, const float* x, const float* y, int n
 #ifdef KCCOT_DEV
 // development build only: device buffer of 4 roles x 64 records x 2 timestamps (clock64) filled by CTA 1
 extern "C" void kccot_debug_set_grad_trace(long long* buf) { kccot::set_grad_trace(buf); }
+// development build only: bounded barrier waits of THIS translation unit report into `buf` (see tc_common.cuh)
+extern "C" int kccot_debug_set_wait_log(unsigned long long* buf) {
+  return (int)cudaMemcpyToSymbol(kccot::tc::s_wait_log, &buf, sizeof(buf));
+}
 #endif

@@ -107,6 +107,11 @@ sqdist_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
+      // drain the asynchronous tcgen05.commit arrivals on empty[] before the CTA may exit (see grad_tcgen05.cu)
+      for (int i = 0; i < kStages; ++i) {
+        tc::mbar_wait(&S.empty[stage], phase ^ 1);
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
     }
   } else if (warp == 1) {
     // ------------------------------- MMA issuer -----------------------------------------------

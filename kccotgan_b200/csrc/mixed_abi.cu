@@ -65,7 +65,6 @@ int kccot_mixed_loss_fwd(const float* real, const float* fake, int nprob, int B,
                          void* stream) {
   KCCOT_CHECK_ARG(saved && loss && ws, "null pointer");
   KCCOT_CHECK_ARG(L >= 0 && eps > 0.f, "bad eps / L");
-  PdlScope pdl(nprob <= kPdlMaxProblems);
   const SavedLayout sl = saved_layout(nprob, B, L);
   char* sv = (char*)saved;
   float* C3 = (float*)(sv + sl.off_C3);
@@ -99,7 +98,6 @@ int kccot_mixed_loss_bwd(const float* gloss, const float* real, const float* fak
                          float* gh_fake, float* gm_real, float* gh_real, float* gm_fake, void* ws, size_t ws_bytes,
                          int flags, void* stream) {
   KCCOT_CHECK_ARG(gloss && saved && ws, "null pointer");
-  PdlScope pdl(nprob <= kPdlMaxProblems);
   const SavedLayout sl = saved_layout(nprob, B, L);
   const char* sv = (const char*)saved;
   const size_t cb_bytes = align_up((size_t)nprob * 3 * B * B * 4, 256);

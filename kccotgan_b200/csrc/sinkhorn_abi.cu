@@ -27,7 +27,6 @@ int kccot_sinkhorn_fwd(const float* C, int nsolve, int B, float eps, int L, int 
   KCCOT_CHECK_ARG(nsolve >= 1 && B >= 1 && L >= 0 && eps > 0.f, "bad sizes: nsolve=%d B=%d L=%d eps=%g", nsolve, B, L,
                   (double)eps);
   cudaStream_t st = (cudaStream_t)stream;
-  PdlScope pdl(nsolve <= 3 * kPdlMaxProblems);
   if (B <= kSmallSinkhornMaxB)
     return launch_sinkhorn_fwd_small(C, nsolve, B, eps, L, Lmin, thresh, exit_on_index, u_hist, v_hist, nits, cost, st);
   if (persist_supported(B, B, L) && L >= 1) {
@@ -56,7 +55,6 @@ int kccot_sinkhorn_bwd(const float* C, int nsolve, int B, float eps, int L, cons
   KCCOT_CHECK_ARG(C && u_hist && v_hist && nits && gcost && Cbar, "null pointer");
   KCCOT_CHECK_ARG(nsolve >= 1 && B >= 1 && L >= 0 && eps > 0.f, "bad sizes");
   cudaStream_t st = (cudaStream_t)stream;
-  PdlScope pdl(nsolve <= 3 * kPdlMaxProblems);
   if (B <= kSmallSinkhornMaxB)
     return launch_sinkhorn_bwd_small(C, nsolve, B, eps, L, u_hist, v_hist, nits, gcost, Cbar, nullptr, st);
   if (persist_supported(B, B, L) && L >= 1) {

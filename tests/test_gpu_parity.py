@@ -659,13 +659,14 @@ def test_batched_entry_point_cfg4_shape(gu):
 
 
 def test_batched_graph_replay_many_problems():
-    """Queued CUDA-graph replays of a many-problem chain (150+ problems: the Sinkhorn kernels run in several waves)
-    must keep making progress: with programmatic launches along the chain they hung on B200 / CUDA 12.9; the
-    library therefore uses plain launches above kPdlMaxProblems.  Runs in a child process under a timeout."""
+    """Queued CUDA-graph replays of a many-problem chain (150+ problems: every kernel runs in several waves) must keep
+    making progress.  They used to hang about once in a few hundred evaluations: the gradient GEMM dealt its boxes
+    round-robin to converter warps that did not own a ring slot, and a parity wait passed a pass early when TMA
+    loads completed out of order (csrc/grad_tcgen05.cu, converter branch).  Runs in a child process under a timeout."""
     import os
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    r = subprocess.run([sys.executable, os.path.join(root, "scripts", "batched_graph_probe2.py"), "160", "2", "1", "60"],
+    r = subprocess.run([sys.executable, os.path.join(root, "scripts", "batched_graph_probe2.py"), "160", "2", "1", "400"],
                        capture_output=True, text=True, timeout=180, cwd=root)
-    assert r.returncode == 0 and "60 alternating replays ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.returncode == 0 and "400 alternating replays ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
