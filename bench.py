@@ -38,6 +38,7 @@ if ROOT not in sys.path:
 S = 1.0 / 15.0
 METRIC = "causal_ot_loss_fwd_bwd_evals_per_sec"
 UNIT = "evals/s"
+NLANES = 6          # independent evaluations in flight (kccotgan_b200.graphed.EvaluationLanes)
 
 
 def parse():
@@ -321,15 +322,49 @@ def run_replica_config(cx, name, kind, steps, smooth):
     launches0 = cx.lib.kccot_launch_count()
     steps_fns[0]()
     per_step = int(cx.lib.kccot_launch_count() - launches0)
-    run = (lambda i: replays[i % nsets]()) if use_graph else (lambda i: steps_fns[i % nsets]())
-    ms, clocks = timed(cx, run, steps)
+    serial = None
+    if use_graph:
+        # independent evaluations replayed round-robin on NLANES streams (see the headline); serial replays beside it
+        nl = min(NLANES, nsets)
+        streams = [torch.cuda.Stream(cx.dev) for _ in range(nl)]
+
+        def run_lanes(i):
+            j = i % nsets
+            with torch.cuda.stream(streams[j % nl]):
+                replays[j]()
+
+        def timed_lanes(n):
+            barrier(cx)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            main = torch.cuda.current_stream(cx.dev)
+            t0 = time.perf_counter()
+            e0.record(main)
+            for s_ in streams:
+                s_.wait_stream(main)
+            for i in range(n):
+                run_lanes(i)
+            for s_ in streams:
+                main.wait_stream(s_)
+            e1.record(main)
+            barrier(cx)
+            t1 = time.perf_counter()
+            return max_over_ranks(cx, e0.elapsed_time(e1)), (cx.sampler.window(t0, t1) if cx.rank == 0 else None)
+
+        timed_lanes(3)
+        ms, clocks = timed_lanes(steps)
+        ms_s, _ = timed(cx, lambda i: replays[i % nsets](), min(steps, 100))
+        serial = cx.world * min(steps, 100) / (ms_s * 1e-3)
+    else:
+        ms, clocks = timed(cx, lambda i: steps_fns[i % nsets](), steps)
     value = cx.world * steps / (ms * 1e-3)
     alg = 20.0 * B * K + 40.0 * B * T * 8 + (24.0 * B * K if smooth else 0.0)    # SURVEY §8d; 1d smoothing: 3 x 8BK
     hbm = float(peaks().get("hbm_gbs", 6650.0))
     ach = alg / (ms * 1e-3 / steps) / 1e9
     out = {"value": value, "unit": UNIT, "steps": steps, "ms_per_step": ms / steps, "scaling": "weak",
            "config": config, "clocks": clocks, "gpu_launches_per_step": per_step,
-           "launch": "CUDA-graph replay" if use_graph else "eager Python calls",
+           "launch": (f"CUDA-graph replay, {min(NLANES, nsets)} independent evaluations in flight on as many streams"
+                      if use_graph else "eager Python calls"),
+           "serial_evals_per_s": serial,
            "step": ("temporal_convolution(real), temporal_convolution(fake) -> compute_sinkhorn_loss -> gradients "
                     "to fake (through the smoothing), h_fake, m_real, h_real, m_fake" if smooth else
                     "compute_sinkhorn_loss -> gradients to fake, h_fake, m_real, h_real, m_fake"),
@@ -544,7 +579,8 @@ def main():
 
     # ---- inputs: NSETS distinct batches so that consecutive steps never find their videos in L2
     in_bytes = 2 * B * K * 4
-    nsets = max(3, int(300e6 // in_bytes) + 1)
+    nsets = max(NLANES, int(300e6 // in_bytes) + 1)
+    nsets = (nsets + NLANES - 1) // NLANES * NLANES          # a multiple of the lanes: a set always replays on the same lane
     sets = []
     for i in range(nsets):
         inp = make_inputs(J=8, kind=args.kind, seed=1 + rank + 1000 * i, device=dev, **cfg)
@@ -582,21 +618,55 @@ def main():
     progress("graphs captured; timing the headline")
     launches0 = lib.kccot_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier(cx)
-    t0 = time.perf_counter()
-    e0.record()
-    for i in range(args.steps):
-        if graphs is not None:
-            graphs[i % nsets].step()
-        else:
-            step(sets[i % nsets])
-    e1.record()
-    barrier(cx)
-    t1 = time.perf_counter()
+
+    def timed_serial(n):
+        barrier(cx)
+        t0 = time.perf_counter()
+        e0.record()
+        for i in range(n):
+            if graphs is not None:
+                graphs[i % nsets].step()
+            else:
+                step(sets[i % nsets])
+        e1.record()
+        barrier(cx)
+        return max_over_ranks(cx, e0.elapsed_time(e1)), t0, time.perf_counter()
+
+    lanes = None
+    if graphs is not None:
+        # Consecutive steps are independent evaluations (own batch, own buffers): they are replayed round-robin on
+        # NLANES streams, so the Sinkhorn kernels of one evaluation (3 SMs) run under the HBM kernels of the others.
+        from kccotgan_b200.graphed import EvaluationLanes
+        lanes = EvaluationLanes(graphs, NLANES)              # input set j always replays on stream j % NLANES
+
+        def timed_lanes(n):
+            barrier(cx)
+            t0 = time.perf_counter()
+            e0.record()
+            lanes.fork()
+            for i in range(n):
+                lanes.submit(i % nsets)
+            lanes.join()
+            e1.record()
+            barrier(cx)
+            return max_over_ranks(cx, e0.elapsed_time(e1)), t0, time.perf_counter()
+
+        timed_lanes(max(3, args.warmup))
+        ms, t0, t1 = timed_lanes(args.steps)
+        ms_serial, _, _ = timed_serial(min(args.steps, 400))
+        serial_evals = world * min(args.steps, 400) / (ms_serial * 1e-3)
+        # the overlapped replays must leave the same results as a serial replay
+        graphs[0].step()
+        torch.cuda.synchronize()
+        assert float(l_e) == float(graphs[0].loss) and torch.equal(g_e[0], graphs[0].grads["fake"])
+        notes["launch"] += (f"; {NLANES} independent evaluations in flight on {NLANES} streams "
+                            "(kccotgan_b200.graphed.EvaluationLanes), results bit-identical to serial replays")
+    else:
+        ms, t0, t1 = timed_serial(args.steps)
+        serial_evals = None
     launches = lib.kccot_launch_count() - launches0
     if graphs is not None:
         launches = args.steps * graphs[0].kernels_per_replay      # replays do not pass through the C-ABI counter
-    ms = max_over_ranks(cx, e0.elapsed_time(e1))
     clocks = cx.sampler.window(t0, t1) if rank == 0 else None
     value = world * args.steps / (ms * 1e-3)
     eager_evals = None
@@ -734,7 +804,8 @@ def main():
             "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32 (cost GEMMs 3xTF32 / 3xFP16-split on tcgen05, fp32 accumulate)",
             "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": roofline, "cpu_baseline": cpu, "eager_evals_per_s": eager_evals, "notes": notes,
+            "roofline": roofline, "cpu_baseline": cpu, "eager_evals_per_s": eager_evals,
+            "serial_evals_per_s": serial_evals, "lanes": NLANES if serial_evals is not None else 1, "notes": notes,
             "configs": other}
     print(json.dumps(line), flush=True)
     if world > 1:

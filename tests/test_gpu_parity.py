@@ -670,3 +670,38 @@ def test_batched_graph_replay_many_problems():
     r = subprocess.run([sys.executable, os.path.join(root, "scripts", "batched_graph_probe2.py"), "160", "2", "1", "400"],
                        capture_output=True, text=True, timeout=180, cwd=root)
     assert r.returncode == 0 and "400 alternating replays ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_evaluation_lanes_match_serial_replays():
+    """Independent evaluations replayed on separate streams (EvaluationLanes) leave exactly the results of serial
+    replays: every evaluator owns its buffers, nothing is shared between lanes."""
+    from kccotgan_b200.graphed import EvaluationLanes, GraphedSinkhornLoss
+    from kccotgan_b200.synthetic import INPUT_ORDER, make_inputs
+    dev = torch.device("cuda", 0)
+    evs = []
+    for i in range(4):
+        inp = make_inputs(B=32, T=6, H=16, W=16, C=3, J=8, ctx=2, kind="uniform" if i % 2 else "video", seed=40 + i,
+                          device=dev)
+        evs.append(GraphedSinkhornLoss(*[inp[k] for k in INPUT_ORDER], S, adopt=True))
+    ref = []
+    for ev in evs:
+        ev.step()
+        torch.cuda.synchronize()
+        ref.append((float(ev.loss), {k: v.clone() for k, v in ev.grads.items()}))
+        ev.loss.zero_()
+        for v in ev.grads.values():
+            v.zero_()
+    lanes = EvaluationLanes(evs, n_lanes=3)
+    assert len(lanes) == 4 and len(lanes.streams) == 3
+    lanes.fork()
+    for rep in range(5):
+        for j in range(len(lanes)):
+            lanes.submit(j)
+    lanes.join()
+    torch.cuda.synchronize()
+    for ev, (l, g) in zip(evs, ref):
+        assert float(ev.loss) == l
+        for k in g:
+            assert torch.equal(ev.grads[k], g[k]), k
+    with pytest.raises(ValueError):
+        EvaluationLanes([])
