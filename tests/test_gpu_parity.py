@@ -682,7 +682,7 @@ def test_evaluation_lanes_match_serial_replays():
     for i in range(4):
         inp = make_inputs(B=32, T=6, H=16, W=16, C=3, J=8, ctx=2, kind="uniform" if i % 2 else "video", seed=40 + i,
                           device=dev)
-        evs.append(GraphedSinkhornLoss(*[inp[k] for k in INPUT_ORDER], S, adopt=True))
+        evs.append(GraphedSinkhornLoss(*[inp[k] for k in INPUT_ORDER], 1.0 / 15.0, adopt=True))
     ref = []
     for ev in evs:
         ev.step()
