@@ -5,25 +5,32 @@
 //     g_r = 2s * sum_c W_rc (z_r - z_c) = -2s * sum_c W'_rc z_c,   W' = W - diag(rowsum(W)),
 // i.e. a skinny GEMM  G[r, col] = sum_c W'[r, c] * Z[c, col]  streamed once over the video columns.
 //
-//   A operand = W', split tf32 hi/lo once per CTA and parked in TENSOR MEMORY (TS-mode tcgen05.mma: lane =
-//               output row, column = contraction index; hi in columns 0-127, lo in 128-255).  An SS-mode
-//               M=128 x N=64 x K=8 instruction re-reads 4 KB of A + 2 KB of B from shared memory per 32
-//               cycles of math (~190 B/clk against a 128 B/clk port, measured as the wall with the clock64
-//               timeline); with A in TMEM only B touches shared memory (<= 64 output rows per launch).
+//   A operand = W', split tf32 hi/lo once per CTA and parked in TENSOR MEMORY (TS-mode tcgen05.mma: lane = A row,
+//               column = contraction index).  An SS-mode M=128 x N=64 x K=8 instruction re-reads 4 KB of A + 2 KB of
+//               B from shared memory per 32 cycles of math (~190 B/clk against a 128 B/clk port, measured as the wall
+//               with the clock64 timeline); with A in TMEM only B touches shared memory.
+//               The launch produces at most 64 output rows, so the 128 A rows of the M = 128 instruction hold BOTH
+//               halves of the split: in every 32-lane quadrant q, lanes 0-15 carry W'hi of output rows 16q..16q+15 and
+//               lanes 16-31 carry W'lo of the same rows.  One instruction then yields W'hi.[Zhi | Zlo] and W'lo.Zhi
+//               at once (the fourth block, W'lo.Zlo, is 2^-22 of the result and is dropped by the epilogue).
 //   B operand = the TMA-loaded video box itself, N-major ("MN-major"): a [rows x 32] fp32 box.  tcgen05
 //               accepts exactly one shared-memory layout for MN-major 32-bit operands,
 //               SWIZZLE_128B_BASE32B (32-byte chunks XOR row%4, 4-row atoms, SBO = 512 B); the boxes
 //               are loaded with the matching TMA mode 128B_ATOM_32B, so no transposition is needed.
+//               B = [Zhi | Zlo]: two N-atoms, LBO = distance between the hi and lo rings.  kind::tf32 reads fp32
+//               words and IGNORES the low 13 mantissa bits, so the raw box serves as Zhi = trunc(Z) as it stands; the
+//               converter warps only write Zlo = Z - trunc(Z) (exact in fp32) into the lo ring.
 //   Stage     = ONE box (8 KB + 8 KB lo at 64 rows): the ring is up to 9 deep, which is what hides the
 //               HBM latency (the first version used two 64 KB stages and starved 44 % of the time).
-//   3xTF32 in TWO instructions per k-step: B = [Zhi | Zlo] (two N-atoms, LBO = distance between the hi and
-//               lo rings), so  W'hi.[Zhi | Zlo]  is one N = 64 instruction; W'lo.Zhi (N = 32) accumulates into
-//               the first 32 columns.  The elected lane needs ~30-40 cycles per tcgen05.mma (descriptor moves
-//               to uniform registers; measured with the clock64 timeline), so fewer, fatter instructions are
-//               what keeps the tensor pipe fed.  fp32 accumulate in TMEM, 4 accumulator buffers of 64 columns.
-//   Epilogue:   TMEM lane = output row: the two warps owning lanes 0-63 add the two column halves, stage the
-//               tile in 128-byte-swizzled shared memory and one TMA store (or reduce-add) writes the
-//               [N x 32] box as full 128-byte row segments.
+//   3xTF32 in ONE instruction per k-step (M = 128, N = 64, K = 8).  The elected lane needs ~30-40 cycles per
+//               tcgen05.mma (descriptor moves to uniform registers; measured with the clock64 timeline) and the
+//               steady state is shared-memory bandwidth (TMA write, converter read / write, operand reads, output
+//               staging): the earlier two-instruction form (N = 64 for W'hi, N = 32 for W'lo, converter rewriting
+//               the hi box rounded) moved 136 KB per 24 KB tile, this one 96 KB.  fp32 accumulate in TMEM, 6
+//               accumulator buffers of 64 columns.
+//   Epilogue:   each of the four epilogue warps owns one quadrant: lanes 0-15 add their two column halves, lanes
+//               16-31 hand W'lo.Zhi down by shuffle; 16 rows per warp are staged in 128-byte-swizzled shared memory
+//               and one TMA store (or reduce-add) writes the [N x 32] box as full 128-byte row segments.
 #include "cost.cuh"
 #include "tc_common.cuh"
 
@@ -38,10 +45,11 @@ constexpr int kConvWarps = kMaxStages;      // ONE converter warp per ring slot 
 constexpr int kConvThreads = kConvWarps * 32;
 constexpr int kEpiWarps = 4;
 constexpr int kThreads = 64 + kConvThreads + kEpiWarps * 32;   // 480
-constexpr int kAccBufs = 4;
+constexpr int kAccBufs = 6;
 constexpr int kAccCols = 64;               // per tile: [W.Zhi | W.Zlo], 32 columns each
-constexpr int kTmemCols = 512;             // W'hi [0,128) | W'lo [128,256) | 4 accumulator buffers x 64 columns
-constexpr int kTmemAcc0 = 256;
+constexpr int kTmemCols = 512;             // W' (hi / lo interleaved by lane) [0,128) | 6 accumulator buffers x 64 columns
+constexpr int kTmemAcc0 = 128;
+constexpr bool kRawHi = true;              // the MMA truncates the raw box itself; converters write only the lo box
 constexpr int kObufBytes = kMaxN * 128;     // one staged output tile
 
 struct Bars {
@@ -136,7 +144,7 @@ grad_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ 
     }
     for (int b = 0; b < kAccBufs; ++b) {
       tc::mbar_init(&bars.acc_full[b], 1);
-      tc::mbar_init(&bars.acc_empty[b], 2);                 // the two warps that own TMEM lanes 0-63
+      tc::mbar_init(&bars.acc_empty[b], kEpiWarps);         // one arrival per quadrant
     }
     tc::mbar_init(&bars.w_ready, kEpiWarps);
     tc::fence_barrier_init();
@@ -149,33 +157,34 @@ grad_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ 
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem = bars.tmem_base;
-  // W' -> tensor memory, by the four epilogue warps (one 32-lane quadrant each: thread = row, 32 contraction
-  // columns per store; tf32 hi to columns [0,128), lo to [128,256); rows >= N and columns >= R are zero).
+  // W' -> tensor memory, by the four epilogue warps (one 32-lane quadrant each).  Lane l of quadrant q holds A row
+  // 16q + (l & 15): its tf32 hi part on lanes 0-15, its lo part on lanes 16-31; 32 contraction columns per store;
+  // rows >= N and columns >= R are zero.  (Both half-warps form the same 16 rows; each keeps its own part.)
   // The TMA producer and the converters do not wait for it: the ring fills while W' is being built; only the
   // MMA issuer waits on w_ready.
   //   Cbar3 == nullptr: W' was built by a separate kernel (generic pair).
   //   Cbar3 != nullptr: mixed loss, W' is formed here from the three cost adjoints (xy, xx, yy):
   //       x-row r:  [ Cxx[r][c] + Cxx[c][r] | Cxy[r][c'] ],   y-row j:  [ Cxy[c][j] | Cyy[j][c'] + Cyy[c'][j] ],
   //       diagonal = -(sum of the row).  The thread holds the whole row, so the row sum needs no reduction;
-  //       the 32-column group that contains the diagonal is stored last (row_off % 32 == 0: warp-uniform).
+  //       the 32-column group that contains the diagonal is stored last (row_off % 16 == 0: warp-uniform).
   if (warp >= 2 + kConvWarps) {
     pdl_wait();      // Cbar3 / W come from the kernel before; the TMA producer and the converters (videos only) run ahead
     const int quadw = warp & 3;
-    const int rr = quadw * 32 + lane;                       // A row = TMEM lane
+    const int rr = quadw * 16 + (lane & 15);                // output row of this lane
+    const bool lo_part = lane >= 16;
+    const uint32_t ta0 = tmem + ((uint32_t)(quadw * 32) << 16);
     if (Cbar3 == nullptr) {
       const float* Wrow = W + ((long long)p * R + row_off + min(rr, N - 1)) * R;
       for (int cg = 0; cg < 128; cg += 32) {
-        float h[32], l[32];
+        float h[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const int c = cg + j;
           const float v = (rr < N && c < R) ? Wrow[c] : 0.f;
-          h[j] = tc::to_tf32(v);
-          l[j] = tc::to_tf32(v - h[j]);
+          const float hh = tc::to_tf32(v);
+          h[j] = lo_part ? tc::to_tf32(v - hh) : hh;
         }
-        const uint32_t ta = tmem + ((uint32_t)(quadw * 32) << 16) + (uint32_t)cg;
-        tc::tmem_st_32x32(ta, h);
-        tc::tmem_st_32x32(ta + 128, l);
+        tc::tmem_st_32x32(ta0 + (uint32_t)cg, h);
       }
     } else {
       const int B = Bx;                                     // mixed loss: Bx == By
@@ -184,7 +193,7 @@ grad_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ 
       const float* Cxx = Cxy + BB;
       const float* Cyy = Cxy + 2 * BB;
       const int r = row_off + min(rr, N - 1);
-      const int dg = ((row_off + quadw * 32) >> 5) & 3;     // group of the diagonal (warp-uniform)
+      const int dg = ((row_off + quadw * 16) >> 5) & 3;     // group of the diagonal (warp-uniform)
       const bool xrow = r < B;
       const int rl = xrow ? r : r - B;
       float d = 0.f;
@@ -192,7 +201,7 @@ grad_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ 
         const int cg = ((dg + 1 + g) & 3) * 32;
         // B % 32 == 0: the whole warp is on x-rows or on y-rows and the whole group on one side of B, so the
         // source block is warp-uniform and the loads are straight-line (row part: 8 x 16 bytes of this
-        // thread's row; column part: 32 loads coalesced across the warp)
+        // thread's row; column part: 32 loads coalesced across each half-warp)
         const bool cx = cg < B;
         const int cgl = cx ? cg : cg - B;
         const float* blk = xrow ? (cx ? Cxx : Cxy) : (cx ? Cxy : Cyy);
@@ -225,16 +234,14 @@ grad_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ 
         }
 #pragma unroll
         for (int j = 0; j < 32; ++j) d += v[j];
-        float h[32], l[32];
+        float h[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const float w = (g == 3 && cg + j == r && rr < N) ? -d : v[j];
-          h[j] = tc::to_tf32(w);
-          l[j] = tc::to_tf32(w - h[j]);
+          const float hh = tc::to_tf32(w);
+          h[j] = lo_part ? tc::to_tf32(w - hh) : hh;
         }
-        const uint32_t ta = tmem + ((uint32_t)(quadw * 32) << 16) + (uint32_t)cg;
-        tc::tmem_st_32x32(ta, h);
-        tc::tmem_st_32x32(ta + 128, l);
+        tc::tmem_st_32x32(ta0 + (uint32_t)cg, h);
       }
     }
     tc::tmem_st_wait();
@@ -272,7 +279,6 @@ grad_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ 
     // ------------------------------- MMA issuer -----------------------------------------------
     if (tc::elect_one()) {
       const uint32_t idesc = tc::make_idesc_tf32(128, kAccCols, /*A K-major*/ 0, /*B MN-major*/ 1);
-      const uint32_t idesc_lo = tc::make_idesc_tf32(128, kCols, 0, 1);
       const uint32_t lbo = (uint32_t)((size_t)nstages * stage_bytes);     // hi box -> lo box of the same stage
       int stage = 0, phase = 0;
       int ab = 0, ab_phase = 0;
@@ -286,7 +292,7 @@ grad_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ 
         for (int half = 0; half < 2; ++half) {
           const int rows = half ? By : Bx;
           if (rows == 0) continue;
-          const uint32_t a_hi = tmem + (uint32_t)(half ? Bx : 0);          // W'hi columns of this half
+          const uint32_t a_w = tmem + (uint32_t)(half ? Bx : 0);           // W' columns of this half
           tc::mbar_wait(&bars.conv[stage], phase);
           KTRACE(1, 0);
           tc::tc_fence_after();
@@ -297,11 +303,8 @@ grad_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ 
 #pragma unroll
           for (int kk = 0; kk < kMaxN / 8; ++kk) {
             if (kk < nk) {
-              const uint64_t b = b0 + (uint32_t)(kk * 64);
-              // columns 0-31 += W'hi.Zhi, columns 32-63 += W'hi.Zlo
-              tc::umma_tf32_ts(d_tmem, a_hi + kk * 8, b, idesc, first ? 0u : 1u);
-              // columns 0-31 += W'lo.Zhi
-              tc::umma_tf32_ts(d_tmem, a_hi + 128 + kk * 8, b, idesc_lo, 1u);
+              // lanes 0-15 of each quadrant: [W'hi.Zhi | W'hi.Zlo]; lanes 16-31: [W'lo.Zhi | (W'lo.Zlo)]
+              tc::umma_tf32_ts(d_tmem, a_w + kk * 8, b0 + (uint32_t)(kk * 64), idesc, first ? 0u : 1u);
               first = false;
             }
           }
@@ -347,10 +350,16 @@ grad_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ 
             const int e = e0 + 32 * u;
             if (e < n16) {
               float4 h, l;
-              h.x = tc::to_tf32(v[u].x); h.y = tc::to_tf32(v[u].y); h.z = tc::to_tf32(v[u].z); h.w = tc::to_tf32(v[u].w);
-              l.x = tc::to_tf32(v[u].x - h.x); l.y = tc::to_tf32(v[u].y - h.y);
-              l.z = tc::to_tf32(v[u].z - h.z); l.w = tc::to_tf32(v[u].w - h.w);
-              tc::sts128(hi + e * 16, h);
+              if (kRawHi) {            // the MMA reads trunc(v) out of the raw box; lo = v - trunc(v) is exact
+                h.x = tc::trunc_tf32(v[u].x); h.y = tc::trunc_tf32(v[u].y);
+                h.z = tc::trunc_tf32(v[u].z); h.w = tc::trunc_tf32(v[u].w);
+                l.x = v[u].x - h.x; l.y = v[u].y - h.y; l.z = v[u].z - h.z; l.w = v[u].w - h.w;
+              } else {
+                h.x = tc::to_tf32(v[u].x); h.y = tc::to_tf32(v[u].y); h.z = tc::to_tf32(v[u].z); h.w = tc::to_tf32(v[u].w);
+                l.x = tc::to_tf32(v[u].x - h.x); l.y = tc::to_tf32(v[u].y - h.y);
+                l.z = tc::to_tf32(v[u].z - h.z); l.w = tc::to_tf32(v[u].w - h.w);
+                tc::sts128(hi + e * 16, h);
+              }
               tc::sts128(lo + e * 16, l);
             }
           }
@@ -363,62 +372,65 @@ grad_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ 
     }
   } else {
     // ------------------------------- epilogue --------------------------------------------------
-    // Output row r lives in TMEM lane r (< 64): only the two warps whose quadrant is 0 or 1 work.
-    // TMEM -> registers -> 128-byte-swizzled staging tile -> one TMA store (or reduce-add) of the
-    // [N x 32] box: full 128-byte row segments reach L2, columns beyond K are clipped by the tensor map.
+    // Quadrant q holds output rows 16q..16q+15: their W'hi products on lanes 0-15, W'lo.Zhi on lanes 16-31.
+    // TMEM -> registers -> (lo lanes hand their part down by shuffle) -> 128-byte-swizzled staging tile -> one
+    // TMA store (or reduce-add) of the [N x 32] box: full 128-byte row segments reach L2, columns beyond K are
+    // clipped by the tensor map.
     const int quad = warp & 3;
-    if (quad < 2) {
-      const int r = quad * 32 + lane;                        // output row of this thread
-      const bool issuer = (quad == 0) && (lane == 0);
-      const bool active = quad * 32 < N;                     // warp-uniform
-      int ab = 0, ab_phase = 0;
-      int ob = 0;
-      for (long long t = t_begin; t < t_end; ++t) {
-        tc::mbar_wait(&bars.acc_full[ab], ab_phase);
-        if (issuer) KTRACE(3, 0);
-        tc::tc_fence_after();
-        float d[32];
-        if (active) {
-          float e[32];
-          const uint32_t ta = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(kTmemAcc0 + ab * kAccCols);
-          tc::tmem_ld_32x32(ta, d);
-          tc::tmem_ld_32x32(ta + 32, e);
-          tc::tmem_ld_wait();
+    const int r = quad * 16 + (lane & 15);                   // output row of this thread
+    const bool hi_lane = lane < 16;
+    const bool issuer = (quad == 0) && (lane == 0);
+    const bool active = quad * 16 < N;                       // warp-uniform
+    int ab = 0, ab_phase = 0;
+    int ob = 0;
+    for (long long t = t_begin; t < t_end; ++t) {
+      tc::mbar_wait(&bars.acc_full[ab], ab_phase);
+      if (issuer) KTRACE(3, 0);
+      tc::tc_fence_after();
+      float d[32];
+      if (active) {
+        float e[32];
+        const uint32_t ta = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(kTmemAcc0 + ab * kAccCols);
+        tc::tmem_ld_32x32(ta, d);
+        tc::tmem_ld_32x32(ta + 32, e);
+        tc::tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) d[j] = neg2s * (d[j] + e[j]);   // (W'.Zhi) + (W'hi.Zlo)
+        for (int j = 0; j < 32; ++j) {
+          const float mine = hi_lane ? d[j] + e[j] : d[j];             // W'hi.(Zhi + Zlo)  |  W'lo.Zhi
+          d[j] = neg2s * (mine + __shfl_down_sync(0xffffffffu, mine, 16));
         }
-        if (issuer) KTRACE(4, 0);      // tmem loaded
-        tc::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) tc::mbar_arrive(&bars.acc_empty[ab]); // the accumulator is free as soon as it is in registers
-        // the staging buffer `ob` was last read by the TMA store issued two tiles ago
-        if (issuer) tc::tma_store_wait_read<1>();
-        if (issuer) KTRACE(4, 1);      // wait_read done
-        tc::named_bar_sync(2, 64);
-        if (issuer) KTRACE(5, 0);      // barrier A passed
-        if (active && r < N) {
-          const uint32_t row = tc::smem_u32(obuf + ob * kObufBytes) + r * 128;
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            tc::sts128(row + ((j ^ (r & 7)) << 4), make_float4(d[4 * j], d[4 * j + 1], d[4 * j + 2], d[4 * j + 3]));
-        }
-        if (issuer) KTRACE(5, 1);      // staged
-        tc::fence_proxy_async_smem();
-        if (issuer) KTRACE(6, 0);      // fenced
-        tc::named_bar_sync(2, 64);
-        if (issuer) KTRACE(6, 1);      // barrier B passed
-        if (issuer) {
-          const int col0 = (int)(t * kCols);
-          if (accumulate) tc::tma_reduce_add_3d(&tmo, obuf + ob * kObufBytes, col0, 0, p);
-          else tc::tma_store_3d(&tmo, obuf + ob * kObufBytes, col0, 0, p);
-          tc::tma_store_commit();
-          KTRACE(3, 1); ++trn;
-        }
-        ob ^= 1;
-        if (++ab == kAccBufs) { ab = 0; ab_phase ^= 1; }
       }
-      if (issuer) tc::tma_store_wait<0>();
+      if (issuer) KTRACE(4, 0);      // tmem loaded
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&bars.acc_empty[ab]); // the accumulator is free as soon as it is in registers
+      // the staging buffer `ob` was last read by the TMA store issued two tiles ago
+      if (issuer) tc::tma_store_wait_read<1>();
+      if (issuer) KTRACE(4, 1);      // wait_read done
+      tc::named_bar_sync(2, kEpiWarps * 32);
+      if (issuer) KTRACE(5, 0);      // barrier A passed
+      if (active && hi_lane && r < N) {
+        const uint32_t row = tc::smem_u32(obuf + ob * kObufBytes) + r * 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          tc::sts128(row + ((j ^ (r & 7)) << 4), make_float4(d[4 * j], d[4 * j + 1], d[4 * j + 2], d[4 * j + 3]));
+      }
+      if (issuer) KTRACE(5, 1);      // staged
+      tc::fence_proxy_async_smem();
+      if (issuer) KTRACE(6, 0);      // fenced
+      tc::named_bar_sync(2, kEpiWarps * 32);
+      if (issuer) KTRACE(6, 1);      // barrier B passed
+      if (issuer) {
+        const int col0 = (int)(t * kCols);
+        if (accumulate) tc::tma_reduce_add_3d(&tmo, obuf + ob * kObufBytes, col0, 0, p);
+        else tc::tma_store_3d(&tmo, obuf + ob * kObufBytes, col0, 0, p);
+        tc::tma_store_commit();
+        KTRACE(3, 1); ++trn;
+      }
+      ob ^= 1;
+      if (++ab == kAccBufs) { ab = 0; ab_phase ^= 1; }
     }
+    if (issuer) tc::tma_store_wait<0>();
   }
   tc::tc_fence_before();
   __syncthreads();

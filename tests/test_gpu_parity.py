@@ -688,9 +688,10 @@ def test_evaluation_lanes_match_serial_replays():
         ev.step()
         torch.cuda.synchronize()
         ref.append((float(ev.loss), {k: v.clone() for k, v in ev.grads.items()}))
-        ev.loss.zero_()
-        for v in ev.grads.values():
-            v.zero_()
+        with torch.no_grad():
+            ev.loss.detach().zero_()
+            for v in ev.grads.values():
+                v.detach().zero_()
     lanes = EvaluationLanes(evs, n_lanes=3)
     assert len(lanes) == 4 and len(lanes.streams) == 3
     lanes.fork()
