@@ -52,7 +52,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eager", action="store_true", help="time eager Python calls instead of CUDA-graph replays")
     ap.add_argument("--cpu-budget-s", type=float, default=25.0)
-    ap.add_argument("--configs", default="cfg1_mmnist,cfg3_bair,cfg4_batched,cfg5_large",
+    ap.add_argument("--configs", default="cfg1_mmnist,cfg2_shared_ctx,cfg3_bair,cfg4_batched,cfg5_large",
                     help="comma list of the other BASELINE configs carried in the line ('' = headline only)")
     return ap.parse_args()
 
@@ -372,6 +372,59 @@ def run_replica_config(cx, name, kind, steps, smooth):
                         "frac": ach / hbm, "algorithmic_bytes_per_step": alg, "traffic": None}}
     if cx.rank == 0:
         out["parity"] = loss_parity(cx, name, kind, "smooth1d_" if smooth else "")
+    return out
+
+
+def run_shared_ctx(cx, name, steps):
+    """the same config on video-like inputs (fake shares its context frames with real, as
+    kernel_train.py:225-226 builds them), plain call against compute_sinkhorn_loss_shared_context."""
+    torch = cx.torch
+    from kccotgan_b200.graphed import EvaluationLanes, GraphedSinkhornLoss
+    from kccotgan_b200.synthetic import INPUT_ORDER, make_inputs
+    cfg, K, config = workload_config(name, "video")
+    B, T, ctx = cfg["B"], cfg["T"], cfg["ctx"]
+    nsets = NLANES
+    out = {"config": config, "ctx_frames": ctx, "unit": UNIT, "steps": steps,
+           "launch": f"CUDA-graph replay, {NLANES} independent evaluations in flight"}
+    ref = None
+    for tag, cf in (("plain", 0), ("shared_context", ctx)):
+        evs = []
+        for i in range(nsets):
+            inp = make_inputs(J=8, kind="video", seed=1 + cx.rank + 1000 * i, device=cx.dev, **cfg)
+            evs.append(GraphedSinkhornLoss(*[inp[k] for k in INPUT_ORDER], S, adopt=True, ctx_frames=cf))
+        lanes = EvaluationLanes(evs, NLANES)
+
+        def run(n):
+            barrier(cx)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            lanes.fork()
+            for i in range(n):
+                lanes.submit(i % nsets)
+            lanes.join()
+            e1.record()
+            barrier(cx)
+            return max_over_ranks(cx, e0.elapsed_time(e1))
+        run(6)
+        ms = run(steps)
+        out[tag] = {"value": cx.world * steps / (ms * 1e-3), "ms_per_step": ms / steps}
+        if ref is None:
+            ref = (float(evs[0].loss), evs[0].grads["fake"][:, :, ctx:].clone())
+        else:
+            out["parity"] = {"checked": True,
+                             "ok": bool(float(evs[0].loss) == ref[0] and torch.equal(evs[0].grads["fake"][:, :, ctx:], ref[1])),
+                             "against": "the plain call on the same inputs: loss and gradient of the predicted frames "
+                                        "bit-identical (tests/test_gpu_parity.py::test_shared_context_hint)"}
+        del evs, lanes
+        torch.cuda.empty_cache()
+    out["value"] = out["shared_context"]["value"]
+    alg_plain = 20.0 * B * K
+    alg_ctx = B * K * (4.0 + 4.0 * (T - ctx) / T + 12.0 * (T - ctx) / T)
+    out["algorithmic_bytes_per_step"] = {"plain": alg_plain, "shared_context": alg_ctx}
+    hbm = float(peaks().get("hbm_gbs", 6650.0))
+    ach = alg_ctx / (out["shared_context"]["ms_per_step"] * 1e-3) / 1e9
+    out["roofline"] = {"bound": "hbm", "scope": "whole step", "achieved": ach, "peak": hbm, "unit": "GB/s",
+                       "frac": ach / hbm, "traffic": None}
     return out
 
 
@@ -751,6 +804,8 @@ def main():
                 other[name] = run_replica_config(cx, name, args.kind, few, smooth=False)
             elif name == "cfg3_bair":
                 other[name] = run_replica_config(cx, name, args.kind, few, smooth=True)
+            elif name == "cfg2_shared_ctx":
+                other[name] = run_shared_ctx(cx, "cfg2_mazes", few)
             elif name == "cfg4_batched":
                 other[name] = run_cfg4(cx, args.kind, max(3, min(args.steps, 20)))
             elif name == "cfg5_large":

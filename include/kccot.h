@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define KCCOT_VERSION 200
+#define KCCOT_VERSION 201
 
 /* error codes */
 #define KCCOT_OK 0
@@ -199,6 +199,31 @@ int kccot_mixed_loss_bwd(const float* gloss, const float* real, const float* fak
                          const float* m_fake, int T, int J, float s, float eps, int L, const void* saved,
                          float* g_real, float* g_fake, float* gh_fake, float* gm_real, float* gh_real,
                          float* gm_fake, void* ws, size_t ws_bytes, int flags, void* stream);
+
+/* Shared context frames — kernel_train.py:225-226 / :267-268 build  real = concat(real_in, real_pred) and
+ * fake = concat(real_in, fake_pred)  along the time axis, so with `--kernel none` the context frames of the two
+ * videos are the same numbers.  The caller states that with (ctx_period, ctx_len): every column c of the flattened
+ * [B, K] rows with (c % ctx_period) < ctx_len holds identical values in real and fake.  For [B,H,T,W,C] videos
+ * ctx_period = T*W*C and ctx_len = ctx_frames*W*C.
+ *   fwd: fake's context columns are never read (the real rows stand in for them): results are bit-identical to
+ *        kccot_mixed_loss_fwd on inputs that keep the promise.
+ *   bwd: g_fake is the gradient with respect to the PREDICTED columns only; its context columns (constants of the
+ *        caller: copies of the data) are not read and not computed; they are set to ZERO (left untouched under
+ *        KCCOT_FLAG_ACCUMULATE).
+ * The tcgen05 path skips the columns when ctx_period and ctx_len are multiples of 32 and K is a multiple of
+ * ctx_period; every other path computes the plain result first, so the outcome is the same on all paths.
+ * Not valid after temporal / 3-D smoothing (which leaks predicted frames into context frames). */
+int kccot_mixed_loss_fwd_ctx(const float* real, const float* fake, int nprob, int B, long long K,
+                             const float* h_fake, const float* m_real, const float* h_real,
+                             const float* m_fake, int T, int J, float s, float eps, int L, void* saved,
+                             float* loss, float* terms, void* ws, size_t ws_bytes, int flags, void* stream,
+                             long long ctx_period, long long ctx_len);
+int kccot_mixed_loss_bwd_ctx(const float* gloss, const float* real, const float* fake, int nprob, int B,
+                             long long K, const float* h_fake, const float* m_real, const float* h_real,
+                             const float* m_fake, int T, int J, float s, float eps, int L, const void* saved,
+                             float* g_real, float* g_fake, float* gh_fake, float* gm_real, float* gh_real,
+                             float* gm_fake, void* ws, size_t ws_bytes, int flags, void* stream,
+                             long long ctx_period, long long ctx_len);
 
 /* ------------------------------------------------------------------------------------------
  * Martingale penalty p_M — gan_utils.py:179-201.  M [B,T,J]; pm [1]; gM [B,T,J] = gpm * dpm/dM.

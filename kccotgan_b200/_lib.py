@@ -58,6 +58,10 @@ SIGNATURES = {
     "kccot_mixed_loss_fwd": (_I, [_P, _P, _I, _I, _LL, _P, _P, _P, _P, _I, _I, _F, _F, _I, _P, _P, _P, _P, _SZ, _I, _P]),
     "kccot_mixed_loss_bwd": (_I, [_P, _P, _P, _I, _I, _LL, _P, _P, _P, _P, _I, _I, _F, _F, _I, _P, _P, _P, _P, _P, _P,
                                   _P, _P, _SZ, _I, _P]),
+    "kccot_mixed_loss_fwd_ctx": (_I, [_P, _P, _I, _I, _LL, _P, _P, _P, _P, _I, _I, _F, _F, _I, _P, _P, _P, _P, _SZ, _I, _P,
+                                      _LL, _LL]),
+    "kccot_mixed_loss_bwd_ctx": (_I, [_P, _P, _P, _I, _I, _LL, _P, _P, _P, _P, _I, _I, _F, _F, _I, _P, _P, _P, _P, _P, _P,
+                                      _P, _P, _SZ, _I, _P, _LL, _LL]),
     "kccot_pm_fwd": (_I, [_P, _I, _I, _I, _F, _F, _P, _P, _P]),
     "kccot_pm_bwd": (_I, [_P, _I, _I, _I, _F, _F, _P, _P, _P, _P]),
     "kccot_smooth_workspace_bytes": (_SZ, [_I, _I, _I, _I, _I, _I]),
@@ -80,8 +84,8 @@ def load():
             fn = getattr(lib, name)          # AttributeError if the .so does not export a declared symbol
             fn.restype = res
             fn.argtypes = args
-        if lib.kccot_version() != 200:
-            raise OSError(f"{LIB_PATH}: ABI version {lib.kccot_version()} != 200; rebuild")
+        if lib.kccot_version() != 201:
+            raise OSError(f"{LIB_PATH}: ABI version {lib.kccot_version()} != 201; rebuild")
         _lib = lib
     return _lib
 

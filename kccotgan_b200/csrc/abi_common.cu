@@ -7,6 +7,7 @@
 namespace kccot {
 static thread_local char g_err[512] = "";
 std::atomic<unsigned long long> g_launches{0};
+thread_local CtxHint t_ctx = {0, 0};
 
 void set_error(const char* fmt, ...) {
   va_list ap;

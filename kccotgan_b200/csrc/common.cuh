@@ -104,6 +104,26 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 }
 int num_sms();
 
+// Shared-context hint of kccot_mixed_loss_fwd_ctx / _bwd_ctx (the reference builds fake = concat(real_in, fake_pred),
+// kernel_train.py:225-226): columns c of the flattened [B, K] rows with (c % period) < len hold the same values in
+// real and fake.  The entry points open a CtxScope; the tensor-core launchers read it (zero = no hint).
+struct CtxHint { long long period, len; };
+extern thread_local CtxHint t_ctx;
+struct CtxScope {
+  CtxHint prev;
+  CtxScope(long long period, long long len) : prev(t_ctx) { t_ctx = CtxHint{period, len}; }
+  ~CtxScope() { t_ctx = prev; }
+};
+// hint in units of 32-column boxes, or false when it cannot be used for this K
+inline bool ctx_boxes(long long K, int* period_boxes, int* len_boxes) {
+  const CtxHint h = t_ctx;
+  if (h.len <= 0 || h.period <= h.len || h.period % 32 || h.len % 32 || K % h.period) return false;
+  if (h.period / 32 > 0x7fffffffLL) return false;
+  *period_boxes = (int)(h.period / 32);
+  *len_boxes = (int)(h.len / 32);
+  return true;
+}
+
 struct SideLane {
   cudaStream_t stream;
   cudaEvent_t fork, join;

@@ -104,7 +104,8 @@ __global__ void __launch_bounds__(128) build_w_pair_kernel(const float* __restri
 __global__ void __launch_bounds__(kThreads, 1)
 grad_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy,
                const __grid_constant__ CUtensorMap tmo, int Bx, int By, long long K, const float* __restrict__ W,
-               const float* __restrict__ Cbar3, int row_off, int N, float neg2s, int accumulate, int nstages, long long* __restrict__ trace) {
+               const float* __restrict__ Cbar3, int row_off, int N, float neg2s, int accumulate, int nstages, int ctx_period,
+               int ctx_len, long long* __restrict__ trace) {
   extern __shared__ uint8_t smem_raw[];
   // align by OFFSET so that the compiler keeps the shared address space (LDS/STS, not generic LD/ST)
   uint8_t* base = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -127,7 +128,15 @@ grad_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ 
 #define KTRACE(role, ev) do { } while (0)
 #endif
   int trn = 0;
-  const long long ntiles = (K + kCols - 1) / kCols;
+  // Shared-context hint (ctx_len != 0): the column tiles whose index modulo ctx_period is below ctx_len are skipped
+  // altogether (their gradient rows are constants of the caller); the loops run over the ACTIVE tiles and
+  // tile_of() maps an active index to its column tile.
+  const int ctx_active = ctx_period - ctx_len;
+  const long long ntiles_all = (K + kCols - 1) / kCols;
+  const long long ntiles = ctx_len ? ntiles_all / ctx_period * ctx_active : ntiles_all;
+  auto tile_of = [&](long long i) -> long long {
+    return ctx_len ? (i / ctx_active) * ctx_period + ctx_len + (i % ctx_active) : i;
+  };
   // each CTA streams a CONTIGUOUS range of column tiles: consecutive 128-byte segments of a row are
   // fetched by the same SM back to back (DRAM page / L2 256-byte promotion locality)
   const long long tpc = (ntiles + gridDim.x - 1) / gridDim.x;
@@ -255,7 +264,7 @@ grad_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ 
     if (tc::elect_one()) {
       int stage = 0, phase = 0;
       for (long long t = t_begin; t < t_end; ++t) {
-        const int col0 = (int)(t * kCols);
+        const int col0 = (int)(tile_of(t) * kCols);
         for (int half = 0; half < 2; ++half) {
           const int rows = half ? By : Bx;
           if (rows == 0) continue;
@@ -421,7 +430,7 @@ grad_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ 
       tc::named_bar_sync(2, kEpiWarps * 32);
       if (issuer) KTRACE(6, 1);      // barrier B passed
       if (issuer) {
-        const int col0 = (int)(t * kCols);
+        const int col0 = (int)(tile_of(t) * kCols);
         if (accumulate) tc::tma_reduce_add_3d(&tmo, obuf + ob * kObufBytes, col0, 0, p);
         else tc::tma_store_3d(&tmo, obuf + ob * kObufBytes, col0, 0, p);
         tc::tma_store_commit();
@@ -480,13 +489,20 @@ static int launch_grad_rows(const CUtensorMap& tmx, const CUtensorMap& tmy, cons
   static size_t attr_smem[kMaxDevices] = {};
   if (smem_attr_needed(attr_smem, g.smem))
     KCCOT_CUDA(cudaFuncSetAttribute(grad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
-  const long long ntiles = (K + kCols - 1) / kCols;
+  long long ntiles = (K + kCols - 1) / kCols;
+  // shared-context hint: only the gradient of the y rows (the fake video) skips the context tiles, and only when it
+  // is written rather than accumulated (the skipped columns are left untouched)
+  int ctx_period = 0, ctx_len = 0;
+  if (row_off == Bx && Bx == By && ctx_boxes(K, &ctx_period, &ctx_len))
+    ntiles = ntiles / ctx_period * (ctx_period - ctx_len);
+  else
+    ctx_period = ctx_len = 0;
   int gx = (int)((num_sms() + nprob - 1) / nprob);
   if (gx > ntiles) gx = (int)ntiles;
   if (gx < 1) gx = 1;
   dim3 grid(gx, nprob);
   KCCOT_CUDA(launch_pdl(grad_tc_kernel, grid, dim3(kThreads), g.smem, st, tmx, tmy, tmo, Bx, By, K, W, Cbar3, row_off, N,
-                        -2.f * s, accumulate, g.nstages, g_grad_trace));
+                        -2.f * s, accumulate, g.nstages, ctx_period, ctx_len, g_grad_trace));
   KCCOT_LAUNCH_CHECK();
   return KCCOT_OK;
 }

@@ -54,7 +54,7 @@ struct __align__(1024) Smem {
 
 __global__ void __launch_bounds__(kThreads, 1)
 sqdist_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy, int Bx, int By,
-                 long long K, int nprob, int ksplit, int kbps, float* __restrict__ part) {
+                 long long K, int nprob, int ksplit, int kbps, float* __restrict__ part, int ctx_period, int ctx_len) {
   extern __shared__ uint8_t smem_raw[];
   // align by OFFSET (not by integer round-trip of the pointer) so that the compiler keeps the shared
   // address space and emits LDS/STS instead of generic LD/ST
@@ -103,7 +103,10 @@ sqdist_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
           tc::mbar_wait(&S.empty[stage], phase ^ 1);
           tc::mbar_arrive_expect_tx(&S.full[stage], (uint32_t)R * kKB * 4);
           tc::tma_load_3d(&tmx, &S.full[stage], &S.hi[stage][0], kb * kKB, 0, p);
-          if (By) tc::tma_load_3d(&tmy, &S.full[stage], &S.hi[stage][Bx * kKB * 4], kb * kKB, 0, p);
+          // shared-context k-blocks: the fake rows equal the real rows, which were requested one instruction ago
+          // (an L2 hit): the fake video's context columns are never read from HBM
+          const bool shared = ctx_len != 0 && (kb % ctx_period) < ctx_len;
+          if (By) tc::tma_load_3d(shared ? &tmx : &tmy, &S.full[stage], &S.hi[stage][Bx * kKB * 4], kb * kKB, 0, p);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -380,7 +383,9 @@ int launch_sqdist_partials_tc(const float* x, const float* y, int nprob, int Bx,
   if (smem_attr_needed(attr_set, smem))
     KCCOT_CUDA(cudaFuncSetAttribute(sqdist_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = min(nprob * ksplit, num_sms());
-  sqdist_tc_kernel<<<grid, kThreads, smem, st>>>(tmx, tmy, Bx, By, K, nprob, ksplit, kbps, part);
+  int ctx_period = 0, ctx_len = 0;
+  if (!(By && Bx == By && ctx_boxes(K, &ctx_period, &ctx_len))) ctx_period = ctx_len = 0;
+  sqdist_tc_kernel<<<grid, kThreads, smem, st>>>(tmx, tmy, Bx, By, K, nprob, ksplit, kbps, part, ctx_period, ctx_len);
   KCCOT_LAUNCH_CHECK();
   return KCCOT_OK;
 }

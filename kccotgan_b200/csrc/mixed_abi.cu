@@ -30,6 +30,23 @@ __global__ void combine_loss_kernel(const float* __restrict__ cost, int nprob, f
   if (terms) { terms[3 * p] = xy; terms[3 * p + 1] = xx; terms[3 * p + 2] = yy; }
 }
 
+// zeroes the context columns of g [rows][period] (rows = nprob * B * K / period); len % 4 == 0 or scalar stores
+__global__ void __launch_bounds__(256) zero_ctx_columns_kernel(float* __restrict__ g, long long rows, long long period,
+                                                               long long len) {
+  if ((len & 3) == 0 && (period & 3) == 0) {
+    const long long per_row = len >> 2, total = rows * per_row;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+      const long long r = i / per_row, c = i - r * per_row;
+      reinterpret_cast<float4*>(g + r * period)[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  } else {
+    const long long total = rows * len;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+      const long long r = i / len, c = i - r * len;
+      g[r * period + c] = 0.f;
+    }
+  }
+}
 __global__ void expand_gloss_kernel(const float* __restrict__ gloss, int nprob, float* __restrict__ gcost) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= nprob) return;
@@ -125,6 +142,41 @@ int kccot_mixed_loss_bwd(const float* gloss, const float* real, const float* fak
   }
   return kccot_mixed_cost_bwd(Cbar3, real, fake, nprob, B, K, h_fake, m_real, h_real, m_fake, T, J, s, g_real, g_fake,
                               gh_fake, gm_real, gh_real, gm_fake, ws2, ws2_bytes, flags, stream);
+}
+
+
+int kccot_mixed_loss_fwd_ctx(const float* real, const float* fake, int nprob, int B, long long K, const float* h_fake,
+                             const float* m_real, const float* h_real, const float* m_fake, int T, int J, float s,
+                             float eps, int L, void* saved, float* loss, float* terms, void* ws, size_t ws_bytes,
+                             int flags, void* stream, long long ctx_period, long long ctx_len) {
+  KCCOT_CHECK_ARG(ctx_period >= 0 && ctx_len >= 0 && (ctx_len == 0 || ctx_len < ctx_period),
+                  "bad shared-context hint: period=%lld len=%lld", ctx_period, ctx_len);
+  CtxScope scope(ctx_period, ctx_len);
+  return kccot_mixed_loss_fwd(real, fake, nprob, B, K, h_fake, m_real, h_real, m_fake, T, J, s, eps, L, saved, loss,
+                              terms, ws, ws_bytes, flags, stream);
+}
+
+int kccot_mixed_loss_bwd_ctx(const float* gloss, const float* real, const float* fake, int nprob, int B, long long K,
+                             const float* h_fake, const float* m_real, const float* h_real, const float* m_fake, int T,
+                             int J, float s, float eps, int L, const void* saved, float* g_real, float* g_fake,
+                             float* gh_fake, float* gm_real, float* gh_real, float* gm_fake, void* ws, size_t ws_bytes,
+                             int flags, void* stream, long long ctx_period, long long ctx_len) {
+  KCCOT_CHECK_ARG(ctx_period >= 0 && ctx_len >= 0 && (ctx_len == 0 || ctx_len < ctx_period),
+                  "bad shared-context hint: period=%lld len=%lld", ctx_period, ctx_len);
+  CtxScope scope(ctx_period, ctx_len);
+  if (int rc = kccot_mixed_loss_bwd(gloss, real, fake, nprob, B, K, h_fake, m_real, h_real, m_fake, T, J, s, eps, L, saved,
+                                    g_real, g_fake, gh_fake, gm_real, gh_real, gm_fake, ws, ws_bytes, flags, stream))
+    return rc;
+  // g_fake's context columns: skipped by the tensor-core path, filled with the plain gradient by the others — zero
+  // either way (left alone by an accumulating call)
+  if (g_fake && ctx_len > 0 && K % ctx_period == 0 && !(flags & KCCOT_FLAG_ACCUMULATE)) {
+    const long long rows = (long long)nprob * B * (K / ctx_period);
+    const long long work = rows * ((ctx_len + 3) / 4);
+    const int grid = (int)((work + 255) / 256 < 148 * 8 ? (work + 255) / 256 : 148 * 8);
+    zero_ctx_columns_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(g_fake, rows, ctx_period, ctx_len);
+    KCCOT_LAUNCH_CHECK();
+  }
+  return KCCOT_OK;
 }
 
 }  // extern "C"

@@ -191,7 +191,8 @@ class MixedLossFn(torch.autograd.Function):
     """One C-ABI call per direction (kccot_mixed_loss_fwd / _bwd)."""
 
     @staticmethod
-    def forward(ctx, real, fake, h_fake, m_real, h_real, m_fake, s, eps, L):
+    def forward(ctx, real, fake, h_fake, m_real, h_real, m_fake, s, eps, L, shared=(0, 0)):
+        """shared = (period, len) in flattened columns: the shared-context hint of kccot_mixed_loss_*_ctx."""
         R, F = _flat_rows(real, "f_real"), _flat_rows(fake, "f_fake")
         if R.shape != F.shape:
             raise ValueError(f"f_real and f_fake must have the same shape, got {tuple(real.shape)} vs "
@@ -212,11 +213,12 @@ class MixedLossFn(torch.autograd.Function):
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         out = torch.empty(4, dtype=torch.float32, device=dev)          # loss | xy, xx, yy
         with torch.cuda.device(dev):
-            _lib.call("kccot_mixed_loss_fwd", _ptr(R), _ptr(F), 1, B, K, _ptr(hs[0]), _ptr(hs[1]), _ptr(hs[2]),
+            _lib.call("kccot_mixed_loss_fwd_ctx", _ptr(R), _ptr(F), 1, B, K, _ptr(hs[0]), _ptr(hs[1]), _ptr(hs[2]),
                       _ptr(hs[3]), T, J, float(s), float(eps), L, _ptr(saved), ctypes.c_void_p(out.data_ptr()),
-                      ctypes.c_void_p(out.data_ptr() + 4), _ptr(ws), ws_bytes, _PATH["flags"], _stream(dev))
+                      ctypes.c_void_p(out.data_ptr() + 4), _ptr(ws), ws_bytes, _PATH["flags"], _stream(dev),
+                      int(shared[0]), int(shared[1]))
         ctx.save_for_backward(R, F, *hs, saved)
-        ctx.meta = (real.shape, fake.shape, float(s), float(eps), L)
+        ctx.meta = (real.shape, fake.shape, float(s), float(eps), L, (int(shared[0]), int(shared[1])))
         loss, terms = out[0], out[1:]
         ctx.mark_non_differentiable(terms)
         ctx.set_materialize_grads(False)          # no zero-fill kernel for the unused gradient of `terms`
@@ -225,13 +227,13 @@ class MixedLossFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gloss, _gterms):
         R, F, h_fake, m_real, h_real, m_fake, saved = ctx.saved_tensors
-        rshape, fshape, s, eps, L = ctx.meta
+        rshape, fshape, s, eps, L, shared = ctx.meta
         B, K = R.shape
         T, J = h_fake.shape[1], h_fake.shape[2]
         dev = R.device
         need = ctx.needs_input_grad
         if gloss is None:                         # loss itself unused downstream
-            return (None,) * 9
+            return (None,) * 10
         gloss = gloss.reshape(1)
         if gloss.dtype != torch.float32 or not gloss.is_contiguous():
             gloss = gloss.float().contiguous()
@@ -244,13 +246,13 @@ class MixedLossFn(torch.autograd.Function):
         _, ws_bytes = _mixed_sizes(B, K, L)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
-            _lib.call("kccot_mixed_loss_bwd", _ptr(gloss), _ptr(R), _ptr(F), 1, B, K, _ptr(h_fake), _ptr(m_real),
+            _lib.call("kccot_mixed_loss_bwd_ctx", _ptr(gloss), _ptr(R), _ptr(F), 1, B, K, _ptr(h_fake), _ptr(m_real),
                       _ptr(h_real), _ptr(m_fake), T, J, s, eps, L, _ptr(saved), _ptr(g_real), _ptr(g_fake),
                       _ptr(gh_fake), _ptr(gm_real), _ptr(gh_real), _ptr(gm_fake), _ptr(ws), ws_bytes, _PATH["flags"],
-                      _stream(dev))
+                      _stream(dev), shared[0], shared[1])
         g_real = g_real.reshape(rshape) if g_real is not None else None
         g_fake = g_fake.reshape(fshape) if g_fake is not None else None
-        return g_real, g_fake, gh_fake, gm_real, gh_real, gm_fake, None, None, None
+        return g_real, g_fake, gh_fake, gm_real, gh_real, gm_fake, None, None, None, None
 
 
 # ------------------------------------------------------------------------------------------------

@@ -95,6 +95,28 @@ def sinkhorn_loss_terms(f_real, f_fake, scaling_coef, h_fake, m_real, h_real, m_
     return MixedLossFn.apply(f_real, f_fake, h_fake, m_real, h_real, m_fake, scaling_coef, epsilon, L)
 
 
+def compute_sinkhorn_loss_shared_context(f_real, f_fake, scaling_coef, h_fake, m_real, h_real, m_fake, ctx_frames,
+                                         epsilon=1.0, L=100):
+    """Not in the reference's API, but in its data flow: kernel_train.py:225-226 / :267-268 build
+    real = concat(real_in, real_pred) and fake = concat(real_in, fake_pred) along the time axis, so with
+    `--kernel none` the first `ctx_frames` frames of the two [B,H,T,W,C] videos are the same numbers.  Stating that
+    lets the kernels skip them: the forward never reads fake's context frames (bit-identical loss), the backward
+    neither reads nor computes the gradient of fake's context frames — they are constants (copies of the data), and
+    the returned gradient is ZERO there instead of the value the reference's tape would hand to the data tensor.
+    Saves ctx/T of the fake video's forward traffic and ctx/T of the whole backward.  Not valid after temporal or
+    3-D smoothing (it leaks predicted frames into the context frames).  Returns (loss, [xy, xx, yy])."""
+    f_real = _check(f_real, "f_real")
+    f_fake = _check(f_fake, "f_fake")
+    if f_real.dim() != 5 or f_fake.dim() != 5:
+        raise ValueError(f"expected [B,H,T,W,C] videos, got {tuple(f_real.shape)} / {tuple(f_fake.shape)}")
+    T, W, C = f_real.shape[2], f_real.shape[3], f_real.shape[4]
+    ctx_frames = int(ctx_frames)
+    if not 0 <= ctx_frames < T:
+        raise ValueError(f"ctx_frames must be in [0, T) = [0, {T}), got {ctx_frames}")
+    return MixedLossFn.apply(f_real, f_fake, h_fake, m_real, h_real, m_fake, scaling_coef, epsilon, L,
+                             (T * W * C, ctx_frames * W * C))
+
+
 def compute_sinkhorn_loss_batched(f_real, f_fake, scaling_coef, h_fake, m_real, h_real, m_fake, epsilon=1.0, L=100):
     """Not in the reference: `nprob` independent (real, fake, h, m) tuples in one call (BASELINE config 4:
     "batched independent Sinkhorn problems").  Every tensor carries a leading problem axis

@@ -16,7 +16,7 @@ _NAMES = ("real", "fake", "h_fake", "m_real", "h_real", "m_fake")
 
 class GraphedSinkhornLoss:
     def __init__(self, real, fake, h_fake, m_real, h_real, m_fake, scaling_coef, want_real_grad=False,
-                 adopt=True, warmup=2):
+                 adopt=True, warmup=2, ctx_frames=0):
         """Captures compute_sinkhorn_loss(...) and its gradients w.r.t. fake, h_fake, m_real, h_real,
         m_fake (and real if asked).  adopt=True uses the given tensors themselves as the static buffers
         (zero copies: later steps must overwrite them in place); adopt=False clones them."""
@@ -25,6 +25,7 @@ class GraphedSinkhornLoss:
             if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float32):
                 raise ValueError(f"{n}: expected a CUDA float32 tensor")
         self.scaling_coef = float(scaling_coef)
+        self.ctx_frames = int(ctx_frames)       # > 0: gan_utils.compute_sinkhorn_loss_shared_context
         bufs = [t.detach() if adopt else t.detach().clone() for t in srcs]
         bufs = [b.contiguous() for b in bufs]
         for b, n in zip(bufs, _NAMES):
@@ -49,8 +50,13 @@ class GraphedSinkhornLoss:
         self.kernels_per_replay = int(_lib.load().kccot_launch_count() - n0)   # libkccot kernels in the graph
 
     def _eager(self):
-        loss = gan_utils.compute_sinkhorn_loss(self.real, self.fake, self.scaling_coef, 0.8, 100, self.h_fake,
-                                               self.m_real, self.h_real, self.m_fake, video=self.real.dim() == 5)
+        if self.ctx_frames > 0:
+            loss, _ = gan_utils.compute_sinkhorn_loss_shared_context(self.real, self.fake, self.scaling_coef,
+                                                                     self.h_fake, self.m_real, self.h_real,
+                                                                     self.m_fake, self.ctx_frames)
+        else:
+            loss = gan_utils.compute_sinkhorn_loss(self.real, self.fake, self.scaling_coef, 0.8, 100, self.h_fake,
+                                                   self.m_real, self.h_real, self.m_fake, video=self.real.dim() == 5)
         return loss, torch.autograd.grad(loss, self._leaves, grad_outputs=self._one)
 
     def step(self):

@@ -706,3 +706,33 @@ def test_evaluation_lanes_match_serial_replays():
             assert torch.equal(ev.grads[k], g[k]), k
     with pytest.raises(ValueError):
         EvaluationLanes([])
+
+
+@pytest.mark.parametrize("B,T,ctx,H,W,C", [(64, 10, 3, 8, 32, 3), (32, 20, 10, 4, 32, 1), (16, 6, 2, 4, 8, 3)])
+def test_shared_context_hint(gu, B, T, ctx, H, W, C):
+    """compute_sinkhorn_loss_shared_context (kernel_train.py:225-226): on videos whose first ctx frames
+    are shared, the loss is bit-identical to the plain call, the gradient of the predicted frames and of h / M is
+    bit-identical, the gradient of fake's context frames is zero; fake's context frames are never read (poisoned
+    with NaN here).  The last shape (W*C = 24, not a multiple of 32) exercises the fallback."""
+    dev = torch.device("cuda", 0)
+    s = 1.0 / 15.0
+    inp = make_inputs(B=B, T=T, H=H, W=W, C=C, J=8, ctx=ctx, kind="video", seed=11, device=dev)
+    lv = [inp[k].clone().requires_grad_(k != "real") for k in INPUT_ORDER]
+    loss0 = gu.compute_sinkhorn_loss(lv[0], lv[1], s, 0.8, 100, *lv[2:], video=True)
+    g0 = torch.autograd.grad(loss0, lv[1:])
+    usable = (W * C) % 32 == 0
+    fake2 = inp["fake"].clone()
+    if usable:
+        fake2[:, :, :ctx] = float("nan")            # must not be read
+    lv2 = [inp["real"].clone(), fake2.requires_grad_(True)] + [inp[k].clone().requires_grad_(True) for k in INPUT_ORDER[2:]]
+    loss1, terms1 = gu.compute_sinkhorn_loss_shared_context(lv2[0], lv2[1], s, *lv2[2:], ctx_frames=ctx)
+    g1 = torch.autograd.grad(loss1, lv2[1:])
+    torch.cuda.synchronize()
+    assert float(loss1) == float(loss0)
+    assert torch.equal(g1[0][:, :, ctx:], g0[0][:, :, ctx:])
+    assert float(g1[0][:, :, :ctx].abs().max()) == 0.0
+    assert float(g0[0][:, :, :ctx].abs().max()) > 0.0
+    for a, b in zip(g1[1:], g0[1:]):
+        assert torch.equal(a, b)
+    with pytest.raises(ValueError):
+        gu.compute_sinkhorn_loss_shared_context(lv2[0], lv2[1], s, *lv2[2:], ctx_frames=T)
