@@ -934,7 +934,8 @@ def stage_times(lib, F, torch, sets, B, K, T, dev, reps=40):
         b.record()
         torch.cuda.synchronize()
         out[name] = a.elapsed_time(b) / reps * 1e3
-    # grad_only still includes the tiny W-build kernel (~2 us); the ncu launch list separates them
+    # "grad_tc_kernel" is the whole call: build_w_image_kernel (64 blocks, ~2 us) + the gradient GEMM; the ncu launch
+    # list separates them
     return out
 
 

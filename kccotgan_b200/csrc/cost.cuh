@@ -65,12 +65,13 @@ int launch_sqdist_partials_tc(const float* x, const float* y, int nprob, int Bx,
                               int ksplit, int kblocks_per_slab, float* part, cudaStream_t st);
 
 // grad_tcgen05.cu — tensor-core adjoint over the stacked rows z = [x; y] (see the file header).
-// Wws: [nprob, R, R] fp32 scratch for the weight matrix.  gx / gy may be null.
+// Wws: tc_grad_ws_bytes(nprob) of scratch for the W' images.  gx / gy may be null.
 #ifdef KCCOT_DEV
 void set_grad_trace(long long* b);
 #endif
 bool tc_grad_supported(const float* x, const float* y, int Bx, int By, long long K, const float* gx,
                        const float* gy);
+size_t tc_grad_ws_bytes(int nprob);      // scratch of the two launchers below (W' images)
 int launch_grad_tc(const float* Cbar3, const float* x, const float* y, int nprob, int Bx, int By, long long K,
                    float s, float* gx, float* gy, int accumulate, float* Wws, cudaStream_t st);
 int launch_grad_pair_tc(const float* Cbar, const float* x, const float* y, int nprob, int Bx, int By, long long K,

@@ -228,7 +228,7 @@ int kccot_mixed_sqdist_partials(const float* real, const float* fake, int nprob,
 size_t kccot_cost_bwd_workspace_bytes(int nprob, int Bx, int By, long long K) {
   if (nprob < 1 || Bx < 1 || By < 1 || K < 1) return 0;
   if (large_path_wanted(Bx, By, false)) return large_cost_bwd_ws_bytes(Bx, By, K, false);
-  return align_up((size_t)nprob * 128 * 128 * sizeof(float) * (Bx + By <= 128 ? 1 : 0) + 256, 256);
+  return align_up((Bx + By <= 128 ? tc_grad_ws_bytes(nprob) : 0) + 256, 256);
 }
 
 int kccot_cost_bwd(const float* Cbar, const float* x, const float* y, int nprob, int Bx, int By, long long K, float s,
@@ -248,7 +248,7 @@ int kccot_cost_bwd(const float* Cbar, const float* x, const float* y, int nprob,
     return KCCOT_OK;
   }
   const bool tc_ok = (flags & 3) != KCCOT_PATH_SIMT && x != y && gx != gy && ws &&
-                     ws_bytes >= (size_t)nprob * 128 * 128 * 4 && tc_grad_supported(x, y, Bx, By, K, gx, gy);
+                     ws_bytes >= tc_grad_ws_bytes(nprob) && tc_grad_supported(x, y, Bx, By, K, gx, gy);
   if ((flags & 3) == KCCOT_PATH_TCGEN05 && !tc_ok) {
     set_error("tcgen05 gradient path requested but unsupported for Bx=%d By=%d K=%lld", Bx, By, K);
     return KCCOT_EUNSUPPORTED;
@@ -274,7 +274,7 @@ int kccot_martingale_bwd(const float* Cbar, const float* h, const float* M, int 
 size_t kccot_mixed_cost_bwd_workspace_bytes(int nprob, int B, long long K) {
   if (nprob < 1 || B < 1 || K < 1) return 0;
   if (large_path_wanted(B, B, false)) return large_cost_bwd_ws_bytes(B, B, K, true);
-  return align_up((size_t)nprob * 128 * 128 * sizeof(float) * (2 * B <= 128 ? 1 : 0) + 256, 256);
+  return align_up((2 * B <= 128 ? tc_grad_ws_bytes(nprob) : 0) + 256, 256);
 }
 
 int kccot_mixed_cost_bwd(const float* Cbar3, const float* real, const float* fake, int nprob, int B, long long K,
@@ -291,7 +291,7 @@ int kccot_mixed_cost_bwd(const float* Cbar3, const float* real, const float* fak
   const float* Cyy = Cbar3 + 2 * BB;
   const bool want_tc = (flags & 3) != KCCOT_PATH_SIMT;
   const bool tc_ok = want_tc && (real != fake) && tc_grad_supported(real, fake, B, B, K, g_real, g_fake) && ws &&
-                     ws_bytes >= (size_t)nprob * 128 * 128 * 4;
+                     ws_bytes >= tc_grad_ws_bytes(nprob);
   if ((flags & 3) == KCCOT_PATH_TCGEN05 && !tc_ok) {
     set_error("tcgen05 gradient path requested but unsupported for B=%d K=%lld", B, K);
     return KCCOT_EUNSUPPORTED;

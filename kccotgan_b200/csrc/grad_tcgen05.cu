@@ -5,10 +5,11 @@
 //     g_r = 2s * sum_c W_rc (z_r - z_c) = -2s * sum_c W'_rc z_c,   W' = W - diag(rowsum(W)),
 // i.e. a skinny GEMM  G[r, col] = sum_c W'[r, c] * Z[c, col]  streamed once over the video columns.
 //
-//   A operand = W', split tf32 hi/lo once per CTA and parked in TENSOR MEMORY (TS-mode tcgen05.mma: lane = A row,
-//               column = contraction index).  An SS-mode M=128 x N=64 x K=8 instruction re-reads 4 KB of A + 2 KB of
-//               B from shared memory per 32 cycles of math (~190 B/clk against a 128 B/clk port, measured as the wall
-//               with the clock64 timeline); with A in TMEM only B touches shared memory.
+//   A operand = W', split tf32 hi/lo ONCE per launch by build_w_image_kernel (a 64-block kernel in front) and parked
+//               in TENSOR MEMORY by every CTA (TS-mode tcgen05.mma: lane = A row, column = contraction index).  An
+//               SS-mode M=128 x N=64 x K=8 instruction re-reads 4 KB of A + 2 KB of B from shared memory per 32
+//               cycles of math (~190 B/clk against a 128 B/clk port, measured as the wall with the clock64
+//               timeline); with A in TMEM only B touches shared memory.
 //               The launch produces at most 64 output rows, so the 128 A rows of the M = 128 instruction hold BOTH
 //               halves of the split: in every 32-lane quadrant q, lanes 0-15 carry W'hi of output rows 16q..16q+15 and
 //               lanes 16-31 carry W'lo of the same rows.  One instruction then yields W'hi.[Zhi | Zlo] and W'lo.Zhi
@@ -59,58 +60,64 @@ struct Bars {
   uint32_t tmem_base;
 };
 
-// builds W' for the mixed loss from Cbar3 [nprob,3,B,B] (xy, xx, yy; weights already applied)
-__global__ void __launch_bounds__(128) build_w_mixed_kernel(const float* __restrict__ Cbar3, int B,
-                                                            float* __restrict__ W) {
-  const int R = 2 * B;
-  const int p = blockIdx.y, r = blockIdx.x, c = threadIdx.x;
-  const long long BB = (long long)B * B;
-  const float* Cxy = Cbar3 + (long long)p * 3 * BB;
-  const float* Cxx = Cxy + BB;
-  const float* Cyy = Cxy + 2 * BB;
-  float w = 0.f;
-  if (c < R && c != r) {
-    if (r < B) w = (c < B) ? Cxx[(long long)r * B + c] + Cxx[(long long)c * B + r] : Cxy[(long long)r * B + (c - B)];
-    else w = (c < B) ? Cxy[(long long)c * B + (r - B)]
-                     : Cyy[(long long)(r - B) * B + (c - B)] + Cyy[(long long)(c - B) * B + (r - B)];
-  }
-  __shared__ float red[4];
-  float s = warp_sum(w);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
-  __syncthreads();
-  const float d = red[0] + red[1] + red[2] + red[3];
-  if (c < R) W[((long long)p * R + r) * R + c] = (c == r) ? -d : w;
-}
-
-// generic pair: W'[i][Bx+j] = Cbar_ij, W'[Bx+j][i] = Cbar_ij
-__global__ void __launch_bounds__(128) build_w_pair_kernel(const float* __restrict__ Cbar, int Bx, int By,
-                                                           float* __restrict__ W) {
+// W' image builder.  One block per (output row rr < 64, row block rb, problem): thread c forms W'[r][c] of the stacked
+// weight matrix (r = row_off + rr; row block 0 = the x rows, 1 = the y rows), the block reduces the row sum (diagonal
+// = -sum), splits into tf32 hi + lo and writes both into the TENSOR-MEMORY IMAGE the gradient kernel loads:
+//     img[p][rb][c / 4][lane][c % 4],  lane = 32 (rr / 16) + (rr % 16) for the hi part, + 16 for the lo part
+// (lane-contiguous 16-byte units: a warp of the gradient kernel reads 512 contiguous bytes per load).  Rows rr >= N and
+// columns c >= R are zero.  148 gradient CTAs used to build the same W' each (~9 600 cycles before their first MMA,
+// arithmetic-bound on four warps); now they copy 64 KB from L2.
+//   kMixed: C = Cbar3 [nprob,3,B,B] (xy, xx, yy; weights already applied):
+//       x-row r:  [ Cxx[r][c] + Cxx[c][r] | Cxy[r][c'] ],   y-row j:  [ Cxy[c][j] | Cyy[j][c'] + Cyy[c'][j] ]
+//   else:   C = Cbar [nprob,Bx,By] of one pair:  W'[i][Bx+j] = W'[Bx+j][i] = Cbar_ij
+constexpr int kImgFloats = 128 * 128;
+template <bool kMixed>
+__global__ void __launch_bounds__(128) build_w_image_kernel(const float* __restrict__ C, int Bx, int By, int rb_first,
+                                                            float* __restrict__ img) {
+  pdl_wait();                    // C comes from the kernel before
+  pdl_launch_dependents();       // the gradient kernel's ring fill may start; it waits for this grid before reading img
+  const int rr = blockIdx.x, rb = rb_first + blockIdx.y, p = blockIdx.z, c = threadIdx.x;
   const int R = Bx + By;
-  const int p = blockIdx.y, r = blockIdx.x, c = threadIdx.x;
-  const float* Cp = Cbar + (long long)p * Bx * By;
+  const int row_off = rb ? Bx : 0, N = rb ? By : Bx;
+  const int r = row_off + rr;
   float w = 0.f;
-  if (c < R) {
-    if (r < Bx && c >= Bx) w = Cp[(long long)r * By + (c - Bx)];
-    else if (r >= Bx && c < Bx) w = Cp[(long long)c * By + (r - Bx)];
+  if (rr < N && c < R && c != r) {
+    if (kMixed) {
+      const int B = Bx;
+      const long long BB = (long long)B * B;
+      const float* Cxy = C + (long long)p * 3 * BB;
+      const float* Cxx = Cxy + BB;
+      const float* Cyy = Cxy + 2 * BB;
+      if (r < B) w = (c < B) ? Cxx[(long long)r * B + c] + Cxx[(long long)c * B + r] : Cxy[(long long)r * B + (c - B)];
+      else w = (c < B) ? Cxy[(long long)c * B + (r - B)]
+                       : Cyy[(long long)(r - B) * B + (c - B)] + Cyy[(long long)(c - B) * B + (r - B)];
+    } else {
+      const float* Cp = C + (long long)p * Bx * By;
+      if (r < Bx && c >= Bx) w = Cp[(long long)r * By + (c - Bx)];
+      else if (r >= Bx && c < Bx) w = Cp[(long long)c * By + (r - Bx)];
+    }
   }
   __shared__ float red[4];
-  float s = warp_sum(w);
+  const float s = warp_sum(w);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
   __syncthreads();
-  const float d = red[0] + red[1] + red[2] + red[3];
-  if (c < R) W[((long long)p * R + r) * R + c] = (c == r) ? -d : w;
+  if (c == r && rr < N) w = -(red[0] + red[1] + red[2] + red[3]);
+  const float hi = tc::to_tf32(w), lo = tc::to_tf32(w - hi);
+  const int lane_hi = 32 * (rr >> 4) + (rr & 15);
+  float* im = img + ((long long)p * 2 + rb) * kImgFloats + (long long)(c >> 2) * 512 + (c & 3);
+  im[lane_hi * 4] = hi;
+  im[(lane_hi + 16) * 4] = lo;
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
 grad_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy,
-               const __grid_constant__ CUtensorMap tmo, int Bx, int By, long long K, const float* __restrict__ W,
-               const float* __restrict__ Cbar3, int row_off, int N, float neg2s, int accumulate, int nstages, int ctx_period,
-               int ctx_len, long long* __restrict__ trace) {
+               const __grid_constant__ CUtensorMap tmo, int Bx, int By, long long K, const float* __restrict__ Wimg,
+               int rb, int N, float neg2s, int accumulate, int nstages, int ctx_period, int ctx_len,
+               long long* __restrict__ trace) {
   extern __shared__ uint8_t smem_raw[];
   // align by OFFSET so that the compiler keeps the shared address space (LDS/STS, not generic LD/ST)
   uint8_t* base = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int R = Bx + By;
   const int rows_max = max(Bx, By);
   const int stage_bytes = rows_max * 128;           // one [rows x 32] box
   // layout: hi[nstages] | lo[nstages] | output staging | barriers   (W' lives in tensor memory)
@@ -166,92 +173,30 @@ grad_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ 
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem = bars.tmem_base;
-  // W' -> tensor memory, by the four epilogue warps (one 32-lane quadrant each).  Lane l of quadrant q holds A row
-  // 16q + (l & 15): its tf32 hi part on lanes 0-15, its lo part on lanes 16-31; 32 contraction columns per store;
-  // rows >= N and columns >= R are zero.  (Both half-warps form the same 16 rows; each keeps its own part.)
-  // The TMA producer and the converters do not wait for it: the ring fills while W' is being built; only the
-  // MMA issuer waits on w_ready.
-  //   Cbar3 == nullptr: W' was built by a separate kernel (generic pair).
-  //   Cbar3 != nullptr: mixed loss, W' is formed here from the three cost adjoints (xy, xx, yy):
-  //       x-row r:  [ Cxx[r][c] + Cxx[c][r] | Cxy[r][c'] ],   y-row j:  [ Cxy[c][j] | Cyy[j][c'] + Cyy[c'][j] ],
-  //       diagonal = -(sum of the row).  The thread holds the whole row, so the row sum needs no reduction;
-  //       the 32-column group that contains the diagonal is stored last (row_off % 16 == 0: warp-uniform).
+  // W' -> tensor memory, by the four epilogue warps (one 32-lane quadrant each): a straight copy of the image that
+  // build_w_image_kernel left in global memory (lane l of quadrant q holds A row 16q + (l & 15): its tf32 hi part on
+  // lanes 0-15, its lo part on lanes 16-31).  The TMA producer and the converters do not wait for it: the ring fills
+  // meanwhile; only the MMA issuer waits on w_ready.
   if (warp >= 2 + kConvWarps) {
-    pdl_wait();      // Cbar3 / W come from the kernel before; the TMA producer and the converters (videos only) run ahead
+    pdl_wait();      // the image comes from the kernel before; the TMA producer and the converters (videos only) run ahead
     const int quadw = warp & 3;
-    const int rr = quadw * 16 + (lane & 15);                // output row of this lane
-    const bool lo_part = lane >= 16;
     const uint32_t ta0 = tmem + ((uint32_t)(quadw * 32) << 16);
-    if (Cbar3 == nullptr) {
-      const float* Wrow = W + ((long long)p * R + row_off + min(rr, N - 1)) * R;
-      for (int cg = 0; cg < 128; cg += 32) {
-        float h[32];
+    const float4* im = reinterpret_cast<const float4*>(Wimg + ((long long)p * 2 + rb) * kImgFloats) + (quadw * 32 + lane);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int c = cg + j;
-          const float v = (rr < N && c < R) ? Wrow[c] : 0.f;
-          const float hh = tc::to_tf32(v);
-          h[j] = lo_part ? tc::to_tf32(v - hh) : hh;
-        }
-        tc::tmem_st_32x32(ta0 + (uint32_t)cg, h);
+    for (int h2 = 0; h2 < 2; ++h2) {                        // 64 contraction columns per round: 16 loads in flight
+      float a[32], b[32];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 t = im[(h2 * 16 + j) * 128];
+        a[4 * j] = t.x; a[4 * j + 1] = t.y; a[4 * j + 2] = t.z; a[4 * j + 3] = t.w;
       }
-    } else {
-      const int B = Bx;                                     // mixed loss: Bx == By
-      const long long BB = (long long)B * B;
-      const float* Cxy = Cbar3 + (long long)p * 3 * BB;
-      const float* Cxx = Cxy + BB;
-      const float* Cyy = Cxy + 2 * BB;
-      const int r = row_off + min(rr, N - 1);
-      const int dg = ((row_off + quadw * 16) >> 5) & 3;     // group of the diagonal (warp-uniform)
-      const bool xrow = r < B;
-      const int rl = xrow ? r : r - B;
-      float d = 0.f;
-      for (int g = 0; g < 4; ++g) {
-        const int cg = ((dg + 1 + g) & 3) * 32;
-        // B % 32 == 0: the whole warp is on x-rows or on y-rows and the whole group on one side of B, so the
-        // source block is warp-uniform and the loads are straight-line (row part: 8 x 16 bytes of this
-        // thread's row; column part: 32 loads coalesced across each half-warp)
-        const bool cx = cg < B;
-        const int cgl = cx ? cg : cg - B;
-        const float* blk = xrow ? (cx ? Cxx : Cxy) : (cx ? Cxy : Cyy);
-        const bool inside = cg < R;                          // groups beyond the stacked rows are zero (no loads)
-        const bool has_row = inside && (xrow || !cx), has_col = inside && (cx || !xrow);
-        float v[32];
-        if (has_row) {
-          const float4* rp = reinterpret_cast<const float4*>(blk + (long long)rl * B + cgl);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 t = rp[j];
-            v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = 0.f;
-        }
-        if (has_col) {
-          const float* cp = blk + (long long)cgl * B + rl;
-          float t[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) t[j] = cp[(long long)j * B];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] += t[j];
-        }
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int c = cg + j;
-          v[j] = (rr < N && c < R && c != r) ? v[j] : 0.f;
-        }
-#pragma unroll
-        for (int j = 0; j < 32; ++j) d += v[j];
-        float h[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float w = (g == 3 && cg + j == r && rr < N) ? -d : v[j];
-          const float hh = tc::to_tf32(w);
-          h[j] = lo_part ? tc::to_tf32(w - hh) : hh;
-        }
-        tc::tmem_st_32x32(ta0 + (uint32_t)cg, h);
+      for (int j = 0; j < 8; ++j) {
+        const float4 t = im[(h2 * 16 + 8 + j) * 128];
+        b[4 * j] = t.x; b[4 * j + 1] = t.y; b[4 * j + 2] = t.z; b[4 * j + 3] = t.w;
       }
+      tc::tmem_st_32x32(ta0 + (uint32_t)(h2 * 64), a);
+      tc::tmem_st_32x32(ta0 + (uint32_t)(h2 * 64 + 32), b);
     }
     tc::tmem_st_wait();
     tc::tc_fence_before();
@@ -478,9 +423,10 @@ bool tc_grad_supported(const float* x, const float* y, int Bx, int By, long long
   return plan_grad(Bx, By, Bx > By ? Bx : By).nstages >= 2;
 }
 
-// W: [nprob, R, R] already holds W' (diagonal = -rowsum)
-static int launch_grad_rows(const CUtensorMap& tmx, const CUtensorMap& tmy, const float* W, const float* Cbar3,
-                            int nprob, int Bx, int By, long long K, float s, int row_off, int N, float* out, int accumulate, cudaStream_t st) {
+// img: the W' images of build_w_image_kernel ([nprob][2][128 x 128] floats); rb = 0: gradient of the x rows, 1: y rows
+static int launch_grad_rows(const CUtensorMap& tmx, const CUtensorMap& tmy, const float* img, int rb, int nprob, int Bx,
+                            int By, long long K, float s, float* out, int accumulate, cudaStream_t st) {
+  const int N = rb ? By : Bx;
   const GradPlan g = plan_grad(Bx, By, N);
   CUtensorMap tmo;     // output [nprob][N][K], box [N x 32], 128-byte swizzle (matches the staging tile)
   if (int rc = encode_tmap_3d(&tmo, out, (uint64_t)K, (uint64_t)N, (uint64_t)nprob, (uint64_t)K * 4, (uint64_t)K * 4 * N,
@@ -490,10 +436,10 @@ static int launch_grad_rows(const CUtensorMap& tmx, const CUtensorMap& tmy, cons
   if (smem_attr_needed(attr_smem, g.smem))
     KCCOT_CUDA(cudaFuncSetAttribute(grad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
   long long ntiles = (K + kCols - 1) / kCols;
-  // shared-context hint: only the gradient of the y rows (the fake video) skips the context tiles, and only when it
-  // is written rather than accumulated (the skipped columns are left untouched)
+  // shared-context hint: only the gradient of the y rows (the fake video) skips the context tiles (the skipped
+  // columns are left untouched)
   int ctx_period = 0, ctx_len = 0;
-  if (row_off == Bx && Bx == By && ctx_boxes(K, &ctx_period, &ctx_len))
+  if (rb == 1 && Bx == By && ctx_boxes(K, &ctx_period, &ctx_len))
     ntiles = ntiles / ctx_period * (ctx_period - ctx_len);
   else
     ctx_period = ctx_len = 0;
@@ -501,41 +447,20 @@ static int launch_grad_rows(const CUtensorMap& tmx, const CUtensorMap& tmy, cons
   if (gx > ntiles) gx = (int)ntiles;
   if (gx < 1) gx = 1;
   dim3 grid(gx, nprob);
-  KCCOT_CUDA(launch_pdl(grad_tc_kernel, grid, dim3(kThreads), g.smem, st, tmx, tmy, tmo, Bx, By, K, W, Cbar3, row_off, N,
+  KCCOT_CUDA(launch_pdl(grad_tc_kernel, grid, dim3(kThreads), g.smem, st, tmx, tmy, tmo, Bx, By, K, img, rb, N,
                         -2.f * s, accumulate, g.nstages, ctx_period, ctx_len, g_grad_trace));
   KCCOT_LAUNCH_CHECK();
   return KCCOT_OK;
 }
 
-int launch_grad_tc(const float* Cbar3, const float* x, const float* y, int nprob, int Bx, int By, long long K, float s,
-                   float* gx, float* gy, int accumulate, float* Wws, cudaStream_t st) {
-  const int R = Bx + By;
-  // Bx == By and Bx % 32 == 0: the gradient kernel forms W' itself (no separate launch); otherwise the
-  // small build kernel runs first
-  const bool fused_w = (Bx == By) && (Bx % 32 == 0) && (reinterpret_cast<uintptr_t>(Cbar3) & 15) == 0;
-  if (!fused_w) {
-    build_w_mixed_kernel<<<dim3(R, nprob), 128, 0, st>>>(Cbar3, Bx, Wws);
-    KCCOT_LAUNCH_CHECK();
-  }
-  const float* Csrc = fused_w ? Cbar3 : nullptr;
-  CUtensorMap tmx, tmy;
-  if (int rc = encode_tmap_3d(&tmx, x, (uint64_t)K, (uint64_t)Bx, (uint64_t)nprob, (uint64_t)K * 4, (uint64_t)K * 4 * Bx,
-                              kBoxCols, (uint32_t)Bx, true))
-    return rc;
-  if (int rc = encode_tmap_3d(&tmy, y, (uint64_t)K, (uint64_t)By, (uint64_t)nprob, (uint64_t)K * 4, (uint64_t)K * 4 * By,
-                              kBoxCols, (uint32_t)By, true))
-    return rc;
-  if (gy)
-    if (int rc = launch_grad_rows(tmx, tmy, Wws, Csrc, nprob, Bx, By, K, s, Bx, By, gy, accumulate, st)) return rc;
-  if (gx)
-    if (int rc = launch_grad_rows(tmx, tmy, Wws, Csrc, nprob, Bx, By, K, s, 0, Bx, gx, accumulate, st)) return rc;
-  return KCCOT_OK;
-}
+size_t tc_grad_ws_bytes(int nprob) { return (size_t)nprob * 2 * kImgFloats * sizeof(float); }
 
-int launch_grad_pair_tc(const float* Cbar, const float* x, const float* y, int nprob, int Bx, int By, long long K,
-                        float s, float* gx, float* gy, int accumulate, float* Wws, cudaStream_t st) {
-  const int R = Bx + By;
-  build_w_pair_kernel<<<dim3(R, nprob), 128, 0, st>>>(Cbar, Bx, By, Wws);
+template <bool kMixed>
+static int launch_grad_common(const float* C, const float* x, const float* y, int nprob, int Bx, int By, long long K,
+                              float s, float* gx, float* gy, int accumulate, float* img, cudaStream_t st) {
+  if (!gx && !gy) return KCCOT_OK;
+  const int rb_first = gx ? 0 : 1, nrb = (gx ? 1 : 0) + (gy ? 1 : 0);
+  KCCOT_CUDA(launch_pdl(build_w_image_kernel<kMixed>, dim3(kMaxN, nrb, nprob), dim3(128), 0, st, C, Bx, By, rb_first, img));
   KCCOT_LAUNCH_CHECK();
   CUtensorMap tmx, tmy;
   if (int rc = encode_tmap_3d(&tmx, x, (uint64_t)K, (uint64_t)Bx, (uint64_t)nprob, (uint64_t)K * 4, (uint64_t)K * 4 * Bx,
@@ -545,10 +470,21 @@ int launch_grad_pair_tc(const float* Cbar, const float* x, const float* y, int n
                               kBoxCols, (uint32_t)By, true))
     return rc;
   if (gy)
-    if (int rc = launch_grad_rows(tmx, tmy, Wws, nullptr, nprob, Bx, By, K, s, Bx, By, gy, accumulate, st)) return rc;
+    if (int rc = launch_grad_rows(tmx, tmy, img, 1, nprob, Bx, By, K, s, gy, accumulate, st)) return rc;
   if (gx)
-    if (int rc = launch_grad_rows(tmx, tmy, Wws, nullptr, nprob, Bx, By, K, s, 0, Bx, gx, accumulate, st)) return rc;
+    if (int rc = launch_grad_rows(tmx, tmy, img, 0, nprob, Bx, By, K, s, gx, accumulate, st)) return rc;
   return KCCOT_OK;
+}
+
+// Wws: tc_grad_ws_bytes(nprob) of scratch for the W' images
+int launch_grad_tc(const float* Cbar3, const float* x, const float* y, int nprob, int Bx, int By, long long K, float s,
+                   float* gx, float* gy, int accumulate, float* Wws, cudaStream_t st) {
+  return launch_grad_common<true>(Cbar3, x, y, nprob, Bx, By, K, s, gx, gy, accumulate, Wws, st);
+}
+
+int launch_grad_pair_tc(const float* Cbar, const float* x, const float* y, int nprob, int Bx, int By, long long K,
+                        float s, float* gx, float* gy, int accumulate, float* Wws, cudaStream_t st) {
+  return launch_grad_common<false>(Cbar, x, y, nprob, Bx, By, K, s, gx, gy, accumulate, Wws, st);
 }
 
 }  // namespace kccot

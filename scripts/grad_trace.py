@@ -26,7 +26,7 @@ t0 = t[t > 0].min()
 names = ["TMA  (slot free -> issued)", "MMA  (operands ready -> committed)", "CONV (box landed -> converted)", "EPI  (acc ready -> store issued)", "EPI2 (tmem loaded -> wait_read done)", "EPI3 (barrier A passed -> staged)", "EPI4 (fenced -> barrier B passed)"]
 for r in range(7):
     print(names[r])
-    for i in range(0, 10):
+    for i in list(range(0, 6)) + list(range(20, 24)) + list(range(46, 52)):
         a, b = int(t[r, i, 0]), int(t[r, i, 1])
         if a == 0: break
         print(f"   {i:3d}: {a - t0:8d} -> {b - t0:8d}  (+{b - a})")
