@@ -255,6 +255,80 @@ __global__ void __launch_bounds__(512, 2) cost_finalize_tiled_kernel(CostBlocks 
   }
 }
 
+// Many problems with one or two k-slabs each (BASELINE config 4: 256 problems, nks = 1): the tile kernel above would
+// launch 64 x nprob x 3 CTAs of 512 threads that each sum ONE partial (49 152 CTAs, 733 us at config 4).  Here one CTA
+// of 256 threads finishes a whole B x B block (B <= 64) of one problem: the h rows and DeltaM rows are staged in shared
+// memory once, thread (i = tid / 4, lane4 = tid % 4) owns row i and the columns lane4, lane4 + 4, ...
+constexpr int kFinSmallMaxB = 64;
+__global__ void __launch_bounds__(256) cost_finalize_small_kernel(CostBlocks blocks, int T, int J, float s) {
+  extern __shared__ float fs_sh[];
+  pdl_wait();                                // the partial tiles come from the kernel before
+  pdl_launch_dependents();
+  const CostBlock& b = blocks.b[blockIdx.y];
+  const int p = blockIdx.x, tid = threadIdx.x;
+  if (blocks.zero != nullptr && blockIdx.y == 0 && tid == 0) blocks.zero[p] = 0;
+  const int tj1 = (T - 1) * J, TJ = T * J, ldh = tj1 | 1;     // odd pitch: rows land in different banks
+  float* hs = fs_sh;                          // [Bx][ldh]
+  float* dms = fs_sh + kFinSmallMaxB * ldh;   // [By][ldh]
+  const int i = tid >> 2, l4 = tid & 3;
+  double acc[kFinSmallMaxB / 4];
+#pragma unroll
+  for (int m = 0; m < kFinSmallMaxB / 4; ++m) acc[m] = 0.0;
+  // ---- distance partials: (P_ij + P'_ji) / 2 summed over the k-slabs in fp64 ----
+  if (i < b.Bx) {
+    const float* pb = b.part + (long long)p * 256 * b.nks * 64;
+#pragma unroll
+    for (int m = 0; m < kFinSmallMaxB / 4; ++m) {
+      const int j = l4 + 4 * m;
+      if (j >= b.By || (b.zero_diag && i == j)) continue;
+      const int gi = b.row_off + i, gj = b.col_off + j;
+      const float* pd = pb + ((long long)((gi >> 3) * 16 + (gj >> 3)) * b.nks) * 64 + (gi & 7) * 8 + (gj & 7);
+      const float* pm = pb + ((long long)((gj >> 3) * 16 + (gi >> 3)) * b.nks) * 64 + (gj & 7) * 8 + (gi & 7);
+      double d = 0.0;
+      for (int ks = 0; ks < b.nks; ++ks) d += (double)pd[ks * 64] + (double)pm[ks * 64];
+      acc[m] = 0.5 * d;
+    }
+  }
+  // ---- martingale terms ----
+  for (int pr = 0; pr < 2; ++pr) {
+    const float* h = pr ? b.h2 : b.h1;
+    const float* M = pr ? b.M2 : b.M1;
+    if (h == nullptr) continue;
+    __syncthreads();
+    for (int e = tid; e < b.Bx * tj1; e += 256) {
+      const int r = e / tj1, c = e - r * tj1;
+      hs[r * ldh + c] = h[((long long)p * b.Bx + r) * TJ + c];
+    }
+    for (int e = tid; e < b.By * tj1; e += 256) {
+      const int r = e / tj1, c = e - r * tj1;
+      const float* Mr = M + ((long long)p * b.By + r) * TJ + c;
+      dms[r * ldh + c] = Mr[J] - Mr[0];
+    }
+    __syncthreads();
+    if (i < b.Bx) {
+      const float* hr = hs + i * ldh;
+#pragma unroll 4
+      for (int m = 0; m < kFinSmallMaxB / 4; ++m) {
+        const int j = l4 + 4 * m;
+        if (j >= b.By) continue;
+        const float* dr = dms + j * ldh;
+        float a0 = 0.f, a1 = 0.f;
+        int c = 0;
+        for (; c + 1 < tj1; c += 2) { a0 = fmaf(hr[c], dr[c], a0); a1 = fmaf(hr[c + 1], dr[c + 1], a1); }
+        if (c < tj1) a0 = fmaf(hr[c], dr[c], a0);
+        acc[m] += (double)a0 + (double)a1;
+      }
+    }
+  }
+  if (i < b.Bx) {
+#pragma unroll
+    for (int m = 0; m < kFinSmallMaxB / 4; ++m) {
+      const int j = l4 + 4 * m;
+      if (j < b.By) b.C[(long long)p * b.C_prob_stride + (long long)i * b.By + j] = (float)((double)s * acc[m]);
+    }
+  }
+}
+
 int launch_cost_finalize(const CostBlocks& blocks, int nblocks, int nprob, int T, int J, float s,
                          cudaStream_t st) {
   int tiles = 0, nks = 1;
@@ -268,6 +342,19 @@ int launch_cost_finalize(const CostBlocks& blocks, int nblocks, int nprob, int T
   for (int i = 0; i < nblocks; ++i) {
     const CostBlock& b = blocks.b[i];
     if (!b.tiled || b.Bx % FT || b.By % FT || b.row_off % FT || b.col_off % FT) all_tiled = false;
+  }
+  bool small_ok = all_tiled && nks <= 2 && nprob >= 16 && (T - 1) * J <= 512;
+  for (int i = 0; i < nblocks; ++i)
+    if (blocks.b[i].Bx > kFinSmallMaxB || blocks.b[i].By > kFinSmallMaxB) small_ok = false;
+  if (small_ok) {
+    const size_t smem = (size_t)2 * kFinSmallMaxB * (((T - 1) * J) | 1) * sizeof(float);
+    static size_t attr_fs[kMaxDevices] = {};
+    if (smem > 48 * 1024 && smem_attr_needed(attr_fs, smem))
+      KCCOT_CUDA(cudaFuncSetAttribute(cost_finalize_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    KCCOT_CUDA(launch_pdl(cost_finalize_small_kernel, dim3((unsigned)nprob, (unsigned)nblocks), dim3(256), smem, st, blocks,
+                          T, J, s));
+    KCCOT_LAUNCH_CHECK();
+    return KCCOT_OK;
   }
   for (int p0 = 0; p0 < nprob; p0 += 65535) {     // grid.y limit
     CostBlocks bl = blocks;

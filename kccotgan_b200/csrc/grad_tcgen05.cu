@@ -443,7 +443,20 @@ static int launch_grad_rows(const CUtensorMap& tmx, const CUtensorMap& tmy, cons
     ntiles = ntiles / ctx_period * (ctx_period - ctx_len);
   else
     ctx_period = ctx_len = 0;
-  int gx = (int)((num_sms() + nprob - 1) / nprob);
+  const int sms = num_sms();
+  int gx = (sms + nprob - 1) / nprob;
+  if ((long long)gx * nprob > sms) {
+    // several waves of CTAs (more problems than SMs): pick the column split whose last wave wastes the fewest SMs,
+    // keeping at least 32 tiles per CTA (256 problems on 148 SMs: 1 range each = 2 waves at 86 %, 4 ranges = 7 at 99 %)
+    int best = gx;
+    double best_eff = 0.0;
+    for (int g = gx; g <= gx + 7 && (long long)g * 32 <= ntiles; ++g) {
+      const long long ctas = (long long)g * nprob, waves = (ctas + sms - 1) / sms;
+      const double eff = (double)ctas / (double)(waves * sms);
+      if (eff > best_eff + 0.02) { best_eff = eff; best = g; }
+    }
+    gx = best;
+  }
   if (gx > ntiles) gx = (int)ntiles;
   if (gx < 1) gx = 1;
   dim3 grid(gx, nprob);

@@ -18,7 +18,7 @@ if [[ $parts == *b* ]]; then
   python bench.py > $out/${tag}_bench.json 2> $out/${tag}_bench.err; echo "bench rc=$?"
 fi
 if [[ $parts == *l* ]]; then
-  timeout 600 $NCU --metrics gpu__time_duration.sum -c 600 --csv --log-file $out/${tag}_launches.csv \
+  timeout 600 $NCU --metrics gpu__time_duration.sum -c 6000 --csv --log-file $out/${tag}_launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $out/${tag}_launches.log 2>&1
   echo "launch list rc=$?"
 fi
