@@ -307,7 +307,7 @@ __global__ void __launch_bounds__(256) cost_finalize_small_kernel(CostBlocks blo
     __syncthreads();
     if (i < b.Bx) {
       const float* hr = hs + i * ldh;
-#pragma unroll 4
+#pragma unroll                                   // (a partial unroll would index acc[] dynamically: local memory)
       for (int m = 0; m < kFinSmallMaxB / 4; ++m) {
         const int j = l4 + 4 * m;
         if (j >= b.By) continue;
@@ -672,7 +672,9 @@ int launch_martingale_jobs(const MartJobs& jobs, int njobs, int nprob, int T, in
     if (jobs.j[i].out) maxrows = max(maxrows, jobs.j[i].nrows);
   if (maxrows == 0) return KCCOT_OK;
   const int TJ = T * J;
-  if (maxrows >= 256 && TJ <= 256) {
+  // many problems per call (BASELINE config 4): the 4-rows-per-CTA kernel below would launch 16 x 4 x nprob CTAs that
+  // each stage all of X (321 us at 256 problems); one 64-row CTA per (job, problem) stages it once
+  if ((maxrows >= 256 || nprob >= 16) && TJ <= 256) {
     const size_t a = (size_t)(TKC * TJ + TR * (TKC + 1)) * sizeof(float), b = (size_t)TR * TJ * sizeof(float);
     const size_t smem_t = a > b ? a : b;
     static size_t attr_t[kMaxDevices] = {};
