@@ -830,7 +830,7 @@ def main():
     alg = {"sqdist_tc_kernel": 8.0 * B * K, "grad_tc_kernel": 12.0 * B * K}
     traffic = {}
     try:        # DRAM bytes per launch from the committed `ncu --set full` capture of the same kernels
-        with open(os.path.join(ROOT, "profiles", "r1_dram_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r2_dram_traffic.json")) as f:
             traffic = json.load(f)
     except OSError:
         pass
@@ -839,7 +839,7 @@ def main():
     achieved = alg[dom] / (dur_us * 1e-6) / 1e9
     roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                 "frac": achieved / hbm_peak, "traffic": traffic.get(dom.split("(")[0]), "peak_source": peak_src,
-                "traffic_source": "profiles/r1_dram_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum of one "
+                "traffic_source": "profiles/r2_dram_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum of one "
                                   "`ncu --set full` capture of the same kernel; not re-measured in this run)",
                 "other_hbm_kernels": {k: {"achieved_GBps": alg[k] / (stages[k] * 1e-6) / 1e9,
                                           "frac": alg[k] / (stages[k] * 1e-6) / 1e9 / hbm_peak} for k in alg if k != dom},

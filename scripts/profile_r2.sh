@@ -22,7 +22,7 @@ if [[ $parts == *l* ]]; then
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $out/${tag}_launches.log 2>&1
   echo "launch list rc=$?"
 fi
-[[ $parts == *2* ]] && full cfg2 'sqdist_tc|cost_finalize_tiled|sinkhorn_fwd_small|sinkhorn_bwd_small|grad_tc|martingale_bwd' 30 8 --steps 2 --warmup 3 --configs ''
+[[ $parts == *2* ]] && full cfg2 'sqdist_tc|cost_finalize_tiled|sinkhorn_fwd_small|sinkhorn_bwd_small|grad_tc|martingale_bwd|build_w_image' 35 7 --steps 2 --warmup 3 --configs ''
 [[ $parts == *3* ]] && full cfg3 'axis_col|axis_tile|tie_sums' 8 8 --steps 2 --warmup 3 --configs cfg3_bair
 if [[ $parts == *5* ]]; then
   full cfg5gemm 'gemm_f16x3' 0 3 --steps 1 --warmup 3 --configs cfg5_large
