@@ -4,7 +4,7 @@ import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from kccotgan_b200.synthetic import CONFIGS
-from kccotgan_b200.train_step import StubDiscriminator, StubGenerator, make_training_steps
+from kccotgan_b200.train_step import GraphedTrainingIteration, StubDiscriminator, StubGenerator, make_training_steps
 
 name = sys.argv[1] if len(sys.argv) > 1 else "cfg2_mazes"
 kernel = sys.argv[2] if len(sys.argv) > 2 else "none"
@@ -30,3 +30,17 @@ for i in range(n): loss, pm = iteration(i)
 e1.record(); torch.cuda.synchronize()
 print(f"{name} kernel={kernel}: {e0.elapsed_time(e1) / n:.3f} ms per training iteration (disc + gen step, stub nets); "
       f"loss {float(loss):.5f} pM {float(pm):.5f}")
+
+# the same iteration recorded into one CUDA graph
+git = GraphedTrainingIteration(gen, dh, dm, data[0][:, :, :ctx], data[0][:, :, ctx:], sigma=5.0, kernel_choice=kernel)
+def giter(i):
+    x = data[i % 4]
+    git.real_in.copy_(x[:, :, :ctx]); git.real_pred.copy_(x[:, :, ctx:])
+    return git.step()
+for i in range(3): giter(i)
+torch.cuda.synchronize()
+e0.record()
+for i in range(n): loss, pm = giter(i)
+e1.record(); torch.cuda.synchronize()
+print(f"{name} kernel={kernel}: {e0.elapsed_time(e1) / n:.3f} ms per GRAPHED training iteration (incl. the copy of the batch "
+      f"into the static buffers); loss {float(loss):.5f} pM {float(pm):.5f}")

@@ -736,3 +736,49 @@ def test_shared_context_hint(gu, B, T, ctx, H, W, C):
         assert torch.equal(a, b)
     with pytest.raises(ValueError):
         gu.compute_sinkhorn_loss_shared_context(lv2[0], lv2[1], s, *lv2[2:], ctx_frames=T)
+
+
+@pytest.mark.parametrize("kernel", ["none", "1d"])
+def test_graphed_training_iteration_matches_eager(kernel):
+    """GraphedTrainingIteration replays exactly what the eager step closures do: same noise stream (default CUDA
+    generator, same seed), same parameters after three iterations, same loss / pM."""
+    from kccotgan_b200.train_step import GraphedTrainingIteration, StubDiscriminator, StubGenerator, make_training_steps
+    B, H, T, ctx, W, C = 8, 16, 6, 2, 16, 3
+    x = [torch.rand(B, H, T, W, C, device="cuda", generator=torch.Generator(device="cuda").manual_seed(70 + i)) for i in range(3)]
+
+    def build():
+        torch.manual_seed(9)
+        gen = StubGenerator(T - ctx, C).cuda()
+        dh, dm = StubDiscriminator(H, W, C).cuda(), StubDiscriminator(H, W, C).cuda()
+        return gen, dh, dm
+
+    # eager run with the capturable optimisers (the default generator drives the noise in both runs)
+    gen, dh, dm = build()
+    disc_step, gen_step = make_training_steps(gen, dh, dm, B, kernel_choice=kernel, gen_lr=1e-2, disc_lr=1e-2, capturable=True)
+    warm = 2
+    torch.manual_seed(123)
+    for _ in range(warm):                                       # mirrors the warm-up iterations of the graphed object
+        disc_step(x[0][:, :, :ctx], x[0][:, :, ctx:], 5.0)
+        gen_step(x[0][:, :, :ctx], x[0][:, :, ctx:], 5.0)
+    outs = []
+    for i in range(3):
+        pm = disc_step(x[i][:, :, :ctx], x[i][:, :, ctx:], 5.0)
+        loss = gen_step(x[i][:, :, :ctx], x[i][:, :, ctx:], 5.0)
+        outs.append((float(loss), float(pm)))
+    ref_params = [p.detach().clone() for m in (gen, dh, dm) for p in m.parameters()]
+
+    gen2, dh2, dm2 = build()
+    torch.manual_seed(123)
+    it = GraphedTrainingIteration(gen2, dh2, dm2, x[0][:, :, :ctx], x[0][:, :, ctx:], sigma=5.0, warmup=warm,
+                                  kernel_choice=kernel, gen_lr=1e-2, disc_lr=1e-2)
+    # (the capture pass itself does not execute and does not advance the generator's offset beyond what replays use)
+    for i in range(3):
+        it.real_in.copy_(x[i][:, :, :ctx])
+        it.real_pred.copy_(x[i][:, :, ctx:])
+        loss, pm = it.step()
+        torch.cuda.synchronize()
+        assert np.isfinite(float(loss)) and np.isfinite(float(pm))
+        assert abs(float(loss) - outs[i][0]) <= 1e-4 * max(1.0, abs(outs[i][0])), (i, float(loss), outs[i])
+        assert abs(float(pm) - outs[i][1]) <= 1e-4 * max(1.0, abs(outs[i][1])), (i, float(pm), outs[i])
+    for a, b in zip(ref_params, [p for m in (gen2, dh2, dm2) for p in m.parameters()]):
+        assert torch.allclose(a, b, rtol=2e-3, atol=2e-5)      # Adam amplifies last-bit differences of atomics-ordered sums
