@@ -543,8 +543,10 @@ __global__ void __launch_bounds__(lpr_of(EPT) * lpr_of(EPT) * EPT) sinkhorn_fwd_
 // HS = true: the whole potential history (nits+1 rows of u and v) is copied to shared memory up
 // front (51 KB at B=64, L=100) so every step reads its operands with LDS; HS = false (history too
 // large): two rows are staged per step with a register prefetch from L2.
-template <int EPT, bool HS>
-__global__ void __launch_bounds__(lpr_of(EPT) * lpr_of(EPT) * EPT) sinkhorn_bwd_small_kernel(
+// MINB = 2 (launches with more problems than SMs, BASELINE config 4): the register allocation is capped so that two
+// CTAs share an SM — the loop is a latency chain, a second CTA fills its bubbles (5.2 waves of one CTA per SM otherwise).
+template <int EPT, bool HS, int MINB>
+__global__ void __launch_bounds__(lpr_of(EPT) * lpr_of(EPT) * EPT, MINB) sinkhorn_bwd_small_kernel(
     const float* __restrict__ C, int B, float eps, int L, const float* __restrict__ u_hist,
     const float* __restrict__ v_hist, const int32_t* __restrict__ nits_in, const float* __restrict__ gcost,
     float* __restrict__ Cbar, const int32_t* __restrict__ only_if, SinkhornMix mix) {
@@ -950,7 +952,7 @@ int launch_sinkhorn_fwd_small(const float* C, int nsolve, int B, float eps, int 
   return launch_fwd_t<32>(C, nsolve, B, eps, L, Lmin, thresh, exit_on_index, u_hist, v_hist, nits, cost, t2, st, mix);
 }
 
-template <int EPT>
+template <int EPT, int MINB>
 static int launch_bwd_t(const float* C, int nsolve, int B, float eps, int L, const float* u_hist, const float* v_hist,
                         const int32_t* nits, const float* gcost, float* Cbar, const int32_t* only_if, int threads,
                         cudaStream_t st, SinkhornMix mix) {
@@ -958,14 +960,14 @@ static int launch_bwd_t(const float* C, int nsolve, int B, float eps, int L, con
   if (hist_bytes <= 160 * 1024) {
     static size_t attr[kMaxDevices] = {};
     if (smem_attr_needed(attr, 160 * 1024))
-      KCCOT_CUDA(cudaFuncSetAttribute(sinkhorn_bwd_small_kernel<EPT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      KCCOT_CUDA(cudaFuncSetAttribute(sinkhorn_bwd_small_kernel<EPT, true, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)(160 * 1024)));
     const size_t tile_bytes = (size_t)(lpr_of(EPT) * EPT) * (lpr_of(EPT) * EPT + 1) * sizeof(float);      // Cbar transposition tile of the epilogue
-    KCCOT_CUDA(launch_pdl(sinkhorn_bwd_small_kernel<EPT, true>, dim3(nsolve), dim3(threads),
+    KCCOT_CUDA(launch_pdl(sinkhorn_bwd_small_kernel<EPT, true, MINB>, dim3(nsolve), dim3(threads),
                           hist_bytes > tile_bytes ? hist_bytes : tile_bytes, st, C, B, eps, L, u_hist, v_hist, nits, gcost,
                           Cbar, only_if, mix));
   } else {
-    KCCOT_CUDA(launch_pdl(sinkhorn_bwd_small_kernel<EPT, false>, dim3(nsolve), dim3(threads), (size_t)0, st, C, B, eps, L,
+    KCCOT_CUDA(launch_pdl(sinkhorn_bwd_small_kernel<EPT, false, MINB>, dim3(nsolve), dim3(threads), (size_t)0, st, C, B, eps, L,
                           u_hist, v_hist, nits, gcost, Cbar, only_if, mix));
   }
   KCCOT_LAUNCH_CHECK();
@@ -979,8 +981,12 @@ int launch_sinkhorn_bwd_small(const float* C, int nsolve, int B, float eps, int 
   // (rank-one accumulation of Cbar), and with two lanes its single warp per scheduler becomes issue-bound
   // (measured: backward chain 72 -> 87 us), while the forward gains (33 -> 28 us)
   const int t4 = ((4 * B + 31) / 32) * 32;
-  if (B <= 32) return launch_bwd_t<8>(C, nsolve, B, eps, L, u_hist, v_hist, nits, gcost, Cbar, only_if, t4, st, mix);
-  return launch_bwd_t<16>(C, nsolve, B, eps, L, u_hist, v_hist, nits, gcost, Cbar, only_if, t4, st, mix);
+  const bool many = nsolve > num_sms();
+  if (B <= 32)
+    return many ? launch_bwd_t<8, 2>(C, nsolve, B, eps, L, u_hist, v_hist, nits, gcost, Cbar, only_if, t4, st, mix)
+                : launch_bwd_t<8, 0>(C, nsolve, B, eps, L, u_hist, v_hist, nits, gcost, Cbar, only_if, t4, st, mix);
+  return many ? launch_bwd_t<16, 2>(C, nsolve, B, eps, L, u_hist, v_hist, nits, gcost, Cbar, only_if, t4, st, mix)
+              : launch_bwd_t<16, 0>(C, nsolve, B, eps, L, u_hist, v_hist, nits, gcost, Cbar, only_if, t4, st, mix);
 }
 
 }  // namespace kccot
