@@ -38,7 +38,7 @@ if ROOT not in sys.path:
 S = 1.0 / 15.0
 METRIC = "causal_ot_loss_fwd_bwd_evals_per_sec"
 UNIT = "evals/s"
-NLANES = 6          # independent evaluations in flight (kccotgan_b200.graphed.EvaluationLanes)
+NLANES = 8          # independent evaluations in flight (kccotgan_b200.graphed.EvaluationLanes)
 
 
 def parse():

@@ -212,12 +212,33 @@ __global__ void __launch_bounds__(1024) axis_tile_kernel(const float* __restrict
 
 __global__ void init_max_kernel(float* m) { *m = __int_as_float(0xff800000); }
 
+// sums[0] = sum gout * out, sums[1] = number of elements at the maximum (out == 1).  16-byte loads, four in flight per
+// thread (the scalar grid-stride version ran at 2.5 TB/s: 29.9 us for the 75.5 MB of config 3).
 __global__ void __launch_bounds__(FT) tie_sums_kernel(const float* __restrict__ gout, const float* __restrict__ out,
                                                       long long n, float* sums) {
   float s = 0.f, c = 0.f;
-  for (long long i = (long long)blockIdx.x * FT + threadIdx.x; i < n; i += (long long)gridDim.x * FT) {
-    const float o = out[i];
-    s = fmaf(gout[i], o, s);
+  const long long stride = (long long)gridDim.x * FT;
+  const long long tid = (long long)blockIdx.x * FT + threadIdx.x;
+  const bool vec = ((reinterpret_cast<uintptr_t>(gout) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+  const long long n4 = vec ? n / 4 : 0;
+  const float4* g4 = reinterpret_cast<const float4*>(gout);
+  const float4* o4 = reinterpret_cast<const float4*>(out);
+  auto acc4 = [&](const float4& g, const float4& o) {
+    s = fmaf(g.x, o.x, s); s = fmaf(g.y, o.y, s); s = fmaf(g.z, o.z, s); s = fmaf(g.w, o.w, s);
+    c += (o.x == 1.0f ? 1.f : 0.f) + (o.y == 1.0f ? 1.f : 0.f) + (o.z == 1.0f ? 1.f : 0.f) + (o.w == 1.0f ? 1.f : 0.f);
+  };
+  long long i = tid;
+  for (; i + 3 * stride < n4; i += 4 * stride) {
+    float4 g[4], o[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { g[u] = __ldg(g4 + i + u * stride); o[u] = __ldg(o4 + i + u * stride); }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) acc4(g[u], o[u]);
+  }
+  for (; i < n4; i += stride) acc4(__ldg(g4 + i), __ldg(o4 + i));
+  for (long long k = 4 * n4 + tid; k < n; k += stride) {
+    const float o = out[k];
+    s = fmaf(gout[k], o, s);
     c += (o == 1.0f) ? 1.f : 0.f;
   }
   s = warp_sum(s);
@@ -345,7 +366,7 @@ int kccot_smooth_bwd(int mode, const float* gout, const float* out, const float*
   const long long nel = (long long)B * H * T * W * C;
   float* sums = (float*)ws;
   KCCOT_CUDA(cudaMemsetAsync(sums, 0, 2 * sizeof(float), st));
-  tie_sums_kernel<<<(unsigned)min((long long)4 * num_sms(), (nel + FT - 1) / FT), FT, 0, st>>>(gout, out, nel, sums);
+  tie_sums_kernel<<<(unsigned)min((long long)8 * num_sms(), (nel / 4 + FT - 1) / FT + 1), FT, 0, st>>>(gout, out, nel, sums);
   KCCOT_LAUNCH_CHECK();
   BwdIn bw{out, maxval, sums};
   BwdIn none{};

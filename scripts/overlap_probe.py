@@ -10,7 +10,7 @@ name = sys.argv[1] if len(sys.argv) > 1 else "cfg2_mazes"
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 1200
 dev = torch.device("cuda", 0)
 cfg = {k: v for k, v in CONFIGS[name].items() if k != "nprob"}
-nsets = 6
+nsets = 12
 graphs = []
 for i in range(nsets):
     inp = make_inputs(J=8, kind="uniform", seed=1 + 1000 * i, device=dev, **cfg)
@@ -21,7 +21,7 @@ for g in graphs:
     g.step()
     torch.cuda.synchronize()
     ref.append((float(g.loss), g.grads["fake"].clone()))
-for ns in (1, 2, 3, 6):
+for ns in (1, 4, 6, 8, 12):
     streams = [torch.cuda.Stream(dev) for _ in range(ns)]
     def run(n):
         for i in range(n):
