@@ -4,6 +4,8 @@
 // kernels in gram_tcgen05.cu replace the distance part when the shape allows; these remain the
 // generic-shape path and the on-device cross-check.
 #include "common.cuh"
+#include <type_traits>
+
 #include "cost.cuh"
 
 namespace kccot {
@@ -593,6 +595,8 @@ __global__ void __launch_bounds__(256) martingale_bwd_kernel(MartJobs jobs, int 
 // thread (ty, tx) owns rows 8 ty .. 8 ty + 7 and columns tx + 32 c.  martingale_bwd_kernel re-reads all of X for
 // every 4 output rows (25 ms at B = 8192); this one reads it once per 64 rows.
 constexpr int TR = 64, TKC = 32;
+// NC = ceil(T*J / 32): column groups a thread really owns (T*J = 160 at config 5: 5 of 8; 80 at config 4: 3 of 8)
+template <int NC>
 __global__ void __launch_bounds__(256) martingale_bwd_tiled_kernel(MartJobs jobs, int T, int J, float s) {
   extern __shared__ float4 sh4[];
   float* sh = reinterpret_cast<float*>(sh4);
@@ -603,43 +607,65 @@ __global__ void __launch_bounds__(256) martingale_bwd_tiled_kernel(MartJobs jobs
   float* Xs = sh;                          // [TKC][TJ]
   float* Ws = sh + TKC * TJ;               // [TR][TKC + 1]
   const int t = threadIdx.x, tx = t & 31, ty = t >> 5;
-  float acc[8][8];
+  float acc[8][NC];
 #pragma unroll
   for (int a = 0; a < 8; ++a)
 #pragma unroll
-    for (int c = 0; c < 8; ++c) acc[a][c] = 0.f;
+    for (int c = 0; c < NC; ++c) acc[a][c] = 0.f;
   for (int src = 0; src < 2; ++src) {
     const float* C = src ? jb.C2 : jb.C1;
     if (C == nullptr) continue;
     C += (long long)p * jb.cprob;
     const float* X = (src ? jb.X2 : jb.X1) + (long long)p * jb.ncontr * TJ;
-    for (int k0 = 0; k0 < jb.ncontr; k0 += TKC) {
+    // software pipeline: the global loads of chunk k0 + TKC are in flight (registers) while chunk k0 is multiplied
+    constexpr int XPT = TKC * 32 * NC / 256, WPT = TR * TKC / 256;          // X values (T*J <= 32 NC) and weights per thread
+    float xr[XPT], wr[WPT];
+    auto fetch = [&](int k0) {
       const int kc = min(TKC, jb.ncontr - k0);
-      __syncthreads();
-      for (int e = t; e < TKC * TJ; e += 256) Xs[e] = (e < kc * TJ) ? X[(long long)k0 * TJ + e] : 0.f;
-      if (!jb.transposed) {
-        for (int e = t; e < TR * TKC; e += 256) {
+#pragma unroll
+      for (int i = 0; i < XPT; ++i) {
+        const int e = t + 256 * i;
+        xr[i] = (e < kc * TJ) ? X[(long long)k0 * TJ + e] : 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < WPT; ++i) {
+        const int e = t + 256 * i;
+        if (!jb.transposed) {
           const int rr = e / TKC, k = e % TKC;
-          Ws[rr * (TKC + 1) + k] = (r0 + rr < jb.nrows && k < kc) ? C[(long long)(r0 + rr) * jb.ld + k0 + k] : 0.f;
-        }
-      } else {
-        for (int e = t; e < TR * TKC; e += 256) {
+          wr[i] = (r0 + rr < jb.nrows && k < kc) ? C[(long long)(r0 + rr) * jb.ld + k0 + k] : 0.f;
+        } else {
           const int k = e / TR, rr = e % TR;
-          Ws[rr * (TKC + 1) + k] = (r0 + rr < jb.nrows && k < kc) ? C[(long long)(k0 + k) * jb.ld + r0 + rr] : 0.f;
+          wr[i] = (r0 + rr < jb.nrows && k < kc) ? C[(long long)(k0 + k) * jb.ld + r0 + rr] : 0.f;
         }
       }
+    };
+    fetch(0);
+    for (int k0 = 0; k0 < jb.ncontr; k0 += TKC) {
       __syncthreads();
+#pragma unroll
+      for (int i = 0; i < XPT; ++i) {
+        const int e = t + 256 * i;
+        if (e < TKC * TJ) Xs[e] = xr[i];
+      }
+#pragma unroll
+      for (int i = 0; i < WPT; ++i) {
+        const int e = t + 256 * i;
+        if (!jb.transposed) Ws[(e / TKC) * (TKC + 1) + e % TKC] = wr[i];
+        else Ws[(e % TR) * (TKC + 1) + e / TR] = wr[i];
+      }
+      __syncthreads();
+      if (k0 + TKC < jb.ncontr) fetch(k0 + TKC);
 #pragma unroll 4
       for (int k = 0; k < TKC; ++k) {
-        float w[8], x[8];
+        float w[8], x[NC];
 #pragma unroll
         for (int a = 0; a < 8; ++a) w[a] = Ws[(ty * 8 + a) * (TKC + 1) + k];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) x[c] = (tx + 32 * c < TJ) ? Xs[k * TJ + tx + 32 * c] : 0.f;
+        for (int c = 0; c < NC; ++c) x[c] = (tx + 32 * c < TJ) ? Xs[k * TJ + tx + 32 * c] : 0.f;
 #pragma unroll
         for (int a = 0; a < 8; ++a)
 #pragma unroll
-          for (int c = 0; c < 8; ++c) acc[a][c] = fmaf(w[a], x[c], acc[a][c]);
+          for (int c = 0; c < NC; ++c) acc[a][c] = fmaf(w[a], x[c], acc[a][c]);
       }
     }
   }
@@ -648,7 +674,7 @@ __global__ void __launch_bounds__(256) martingale_bwd_tiled_kernel(MartJobs jobs
 #pragma unroll
   for (int a = 0; a < 8; ++a)
 #pragma unroll
-    for (int c = 0; c < 8; ++c)
+    for (int c = 0; c < NC; ++c)
       if (tx + 32 * c < TJ) sh[(ty * 8 + a) * TJ + tx + 32 * c] = acc[a][c];
   __syncthreads();
   for (int e = t; e < TR * TJ; e += 256) {
@@ -677,11 +703,20 @@ int launch_martingale_jobs(const MartJobs& jobs, int njobs, int nprob, int T, in
   if ((maxrows >= 256 || nprob >= 16) && TJ <= 256) {
     const size_t a = (size_t)(TKC * TJ + TR * (TKC + 1)) * sizeof(float), b = (size_t)TR * TJ * sizeof(float);
     const size_t smem_t = a > b ? a : b;
-    static size_t attr_t[kMaxDevices] = {};
-    if (smem_t > 48 * 1024 && smem_attr_needed(attr_t, smem_t))
-      KCCOT_CUDA(cudaFuncSetAttribute(martingale_bwd_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
-    martingale_bwd_tiled_kernel<<<dim3((maxrows + TR - 1) / TR, njobs, nprob), 256, smem_t, st>>>(jobs, T, J, s);
-    KCCOT_LAUNCH_CHECK();
+    const dim3 grid((maxrows + TR - 1) / TR, njobs, nprob);
+    auto go = [&](auto nc_tag) -> int {
+      constexpr int NC = decltype(nc_tag)::value;
+      static size_t attr_t[kMaxDevices] = {};
+      if (smem_t > 48 * 1024 && smem_attr_needed(attr_t, smem_t))
+        KCCOT_CUDA(cudaFuncSetAttribute(martingale_bwd_tiled_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
+      martingale_bwd_tiled_kernel<NC><<<grid, 256, smem_t, st>>>(jobs, T, J, s);
+      KCCOT_LAUNCH_CHECK();
+      return KCCOT_OK;
+    };
+    const int nc = (TJ + 31) / 32;
+    if (nc <= 3) { if (int rc = go(std::integral_constant<int, 3>{})) return rc; }
+    else if (nc <= 5) { if (int rc = go(std::integral_constant<int, 5>{})) return rc; }
+    else { if (int rc = go(std::integral_constant<int, 8>{})) return rc; }
     return KCCOT_OK;
   }
   const size_t smem = (size_t)(2 * MKC * TJ + 2 * MR * MKC) * sizeof(float);
