@@ -263,14 +263,16 @@ __global__ void __launch_bounds__(512, 2) cost_finalize_tiled_kernel(CostBlocks 
 // memory once, thread (i = tid / 4, lane4 = tid % 4) owns row i and the columns lane4, lane4 + 4, ...
 constexpr int kFinSmallMaxB = 64;
 __global__ void __launch_bounds__(256) cost_finalize_small_kernel(CostBlocks blocks, int T, int J, float s) {
-  extern __shared__ float fs_sh[];
+  extern __shared__ __align__(16) float fs_sh[];
   pdl_wait();                                // the partial tiles come from the kernel before
   pdl_launch_dependents();
   const CostBlock& b = blocks.b[blockIdx.y];
   const int p = blockIdx.x, tid = threadIdx.x;
   if (blocks.zero != nullptr && blockIdx.y == 0 && tid == 0) blocks.zero[p] = 0;
-  const int tj1 = (T - 1) * J, TJ = T * J, ldh = tj1 | 1;     // odd pitch: rows land in different banks
-  float* hs = fs_sh;                          // [Bx][ldh]
+  // row pitch: a multiple of 4 floats (16-byte loads along the contraction) that is 12 mod 32 when (T-1)J is a
+  // multiple of 8, so the eight rows of a warp's 16-byte loads fall into different banks
+  const int tj1 = (T - 1) * J, TJ = T * J, tj4 = (tj1 + 3) & ~3, ldh = tj4 + 4;
+  float* hs = fs_sh;                          // [Bx][ldh], zero-padded to tj4
   float* dms = fs_sh + kFinSmallMaxB * ldh;   // [By][ldh]
   const int i = tid >> 2, l4 = tid & 3;
   double acc[kFinSmallMaxB / 4];
@@ -291,35 +293,39 @@ __global__ void __launch_bounds__(256) cost_finalize_small_kernel(CostBlocks blo
       acc[m] = 0.5 * d;
     }
   }
-  // ---- martingale terms ----
+  // ---- martingale terms: thread (i, l4) owns row i and the columns l4, l4 + 4, ...; one 16-byte load of its h row
+  //      and one per column feed 4 FMAs each ----
   for (int pr = 0; pr < 2; ++pr) {
     const float* h = pr ? b.h2 : b.h1;
     const float* M = pr ? b.M2 : b.M1;
     if (h == nullptr) continue;
     __syncthreads();
-    for (int e = tid; e < b.Bx * tj1; e += 256) {
-      const int r = e / tj1, c = e - r * tj1;
-      hs[r * ldh + c] = h[((long long)p * b.Bx + r) * TJ + c];
+    for (int e = tid; e < b.Bx * tj4; e += 256) {
+      const int r = e / tj4, c = e - r * tj4;
+      hs[r * ldh + c] = (c < tj1) ? h[((long long)p * b.Bx + r) * TJ + c] : 0.f;
     }
-    for (int e = tid; e < b.By * tj1; e += 256) {
-      const int r = e / tj1, c = e - r * tj1;
+    for (int e = tid; e < b.By * tj4; e += 256) {
+      const int r = e / tj4, c = e - r * tj4;
       const float* Mr = M + ((long long)p * b.By + r) * TJ + c;
-      dms[r * ldh + c] = Mr[J] - Mr[0];
+      dms[r * ldh + c] = (c < tj1) ? Mr[J] - Mr[0] : 0.f;
     }
     __syncthreads();
     if (i < b.Bx) {
-      const float* hr = hs + i * ldh;
-#pragma unroll                                   // (a partial unroll would index acc[] dynamically: local memory)
-      for (int m = 0; m < kFinSmallMaxB / 4; ++m) {
-        const int j = l4 + 4 * m;
-        if (j >= b.By) continue;
-        const float* dr = dms + j * ldh;
-        float a0 = 0.f, a1 = 0.f;
-        int c = 0;
-        for (; c + 1 < tj1; c += 2) { a0 = fmaf(hr[c], dr[c], a0); a1 = fmaf(hr[c + 1], dr[c + 1], a1); }
-        if (c < tj1) a0 = fmaf(hr[c], dr[c], a0);
-        acc[m] += (double)a0 + (double)a1;
+      float a[kFinSmallMaxB / 4];
+#pragma unroll
+      for (int m = 0; m < kFinSmallMaxB / 4; ++m) a[m] = 0.f;
+      const float4* hr = reinterpret_cast<const float4*>(hs + i * ldh);
+      for (int c4 = 0; c4 < tj4 / 4; ++c4) {
+        const float4 hv = hr[c4];
+#pragma unroll
+        for (int m = 0; m < kFinSmallMaxB / 4; ++m) {
+          const int j = min(l4 + 4 * m, b.By - 1);
+          const float4 dv = reinterpret_cast<const float4*>(dms + j * ldh)[c4];
+          a[m] = fmaf(hv.x, dv.x, fmaf(hv.y, dv.y, fmaf(hv.z, dv.z, fmaf(hv.w, dv.w, a[m]))));
+        }
       }
+#pragma unroll
+      for (int m = 0; m < kFinSmallMaxB / 4; ++m) acc[m] += (double)a[m];
     }
   }
   if (i < b.Bx) {
@@ -345,11 +351,11 @@ int launch_cost_finalize(const CostBlocks& blocks, int nblocks, int nprob, int T
     const CostBlock& b = blocks.b[i];
     if (!b.tiled || b.Bx % FT || b.By % FT || b.row_off % FT || b.col_off % FT) all_tiled = false;
   }
-  bool small_ok = all_tiled && nks <= 2 && nprob >= 16 && (T - 1) * J <= 512;
+  bool small_ok = all_tiled && nks <= 4 && nprob >= 16 && (T - 1) * J <= 512;
   for (int i = 0; i < nblocks; ++i)
     if (blocks.b[i].Bx > kFinSmallMaxB || blocks.b[i].By > kFinSmallMaxB) small_ok = false;
   if (small_ok) {
-    const size_t smem = (size_t)2 * kFinSmallMaxB * (((T - 1) * J) | 1) * sizeof(float);
+    const size_t smem = (size_t)2 * kFinSmallMaxB * ((((T - 1) * J + 3) & ~3) + 4) * sizeof(float);
     static size_t attr_fs[kMaxDevices] = {};
     if (smem > 48 * 1024 && smem_attr_needed(attr_fs, smem))
       KCCOT_CUDA(cudaFuncSetAttribute(cost_finalize_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -351,7 +351,7 @@ void tc_sqdist_plan(int nprob, int R, long long K, int* ksplit, int* kbps) {
   // at least 8 k-blocks (128 KB of input) per item so the 64 KB partial tile stays amortised
   int best = 1;
   double best_eff = 0.0;
-  const int max_split = max(1, min(nkb / 8, (4 * sms + nprob - 1) / nprob));
+  const int max_split = max(1, min(nkb / 8, (8 * sms + nprob - 1) / nprob));
   for (int s = 1; s <= max_split; ++s) {
     const long long work = (long long)nprob * s;
     const long long waves = (work + sms - 1) / sms;
