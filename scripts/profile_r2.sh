@@ -19,7 +19,7 @@ if [[ $parts == *b* ]]; then
 fi
 if [[ $parts == *l* ]]; then
   timeout 600 $NCU --metrics gpu__time_duration.sum -c 6000 --csv --log-file $out/${tag}_launches.csv \
-    python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $out/${tag}_launches.log 2>&1
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline ${LAUNCH_CONFIGS:+--configs $LAUNCH_CONFIGS} > $out/${tag}_launches.log 2>&1
   echo "launch list rc=$?"
 fi
 [[ $parts == *2* ]] && full cfg2 'sqdist_tc|cost_finalize_tiled|sinkhorn_fwd_small|sinkhorn_bwd_small|grad_tc|martingale_bwd|build_w_image' 35 7 --steps 2 --warmup 3 --configs ''
