@@ -247,6 +247,44 @@ def test_mixed_loss_batched_abi(nprob, B, T, D, path):
             assert e < GRAD_TOL, (q, n, e)
 
 
+@pytest.mark.parametrize("nprob,Bx,By,T,D,two_pairs", [(20, 24, 40, 5, 64, True), (33, 64, 64, 4, 96, True),
+                                                       (16, 8, 16, 3, 32, False)])
+def test_cost_many_problems_abi(nprob, Bx, By, T, D, two_pairs):
+    """kccot_cost_fwd with many problems per call (the per-problem finalize kernel: one and two martingale pairs,
+    rectangular blocks): sampled problems against single-problem calls (tile finalize kernel) and against fp64
+    s * (|x_i - y_j|^2 + sum_pairs sum_t h_i,t (M_j,t+1 - M_j,t))  (gan_utils.py:14-17, :34-38, :59-66)."""
+    from kccotgan_b200 import _lib, functional as F
+    lib = _lib.load()
+    J, s = 5, 1.0 / 9.0
+    K = T * D
+    g = torch.Generator().manual_seed(7 * nprob + Bx)
+    x = torch.rand((nprob, Bx, T, D), generator=g)
+    y = torch.rand((nprob, By, T, D), generator=g)
+    h1, h2 = [torch.sigmoid(torch.randn((nprob, Bx, T, J), generator=g)) for _ in range(2)]     # row-indexed
+    M1, M2 = [torch.sigmoid(torch.randn((nprob, By, T, J), generator=g)) for _ in range(2)]     # column-indexed
+    dx, dy, dh1, dM1, dh2, dM2 = [t.cuda().contiguous() for t in (x, y, h1, M1, h2, M2)]
+    p, st = F._ptr, F._stream(dx.device)
+    C = torch.full((nprob, Bx, By), float("nan"), device="cuda")
+    ws = torch.empty(lib.kccot_cost_workspace_bytes(nprob, Bx, By, K), dtype=torch.uint8, device="cuda")
+    _lib.call("kccot_cost_fwd", p(dx), p(dy), nprob, Bx, By, K, p(dh1), p(dM1), p(dh2) if two_pairs else None,
+              p(dM2) if two_pairs else None, T, J, s, p(C), p(ws), ws.numel(), 0, st)
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(C).all())
+    for q in (0, nprob // 2, nprob - 1):
+        Cq = torch.empty((Bx, By), device="cuda")
+        wsq = torch.empty(lib.kccot_cost_workspace_bytes(1, Bx, By, K), dtype=torch.uint8, device="cuda")
+        _lib.call("kccot_cost_fwd", p(dx[q]), p(dy[q]), 1, Bx, By, K, p(dh1[q]), p(dM1[q]), p(dh2[q]) if two_pairs else None,
+                  p(dM2[q]) if two_pairs else None, T, J, s, p(Cq), p(wsq), wsq.numel(), 0, st)
+        torch.cuda.synchronize()
+        assert maxrel(C[q].cpu(), Cq.cpu()) < COST_TOL
+        xx, yy = x[q].numpy().astype(np.float64).reshape(Bx, -1), y[q].numpy().astype(np.float64).reshape(By, -1)
+        ref = (xx * xx).sum(1)[:, None] + (yy * yy).sum(1)[None, :] - 2.0 * xx @ yy.T
+        for hh, MM in ((h1, M1), (h2, M2))[: 2 if two_pairs else 1]:
+            hq, Mq = hh[q].numpy().astype(np.float64), MM[q].numpy().astype(np.float64)
+            ref = ref + np.einsum("itk,jtk->ij", hq[:, :-1], Mq[:, 1:] - Mq[:, :-1])
+        assert maxrel(C[q].cpu(), s * ref) < COST_TOL
+
+
 # ---------------------------------------------------------------------------------------------
 # Sinkhorn kernels in isolation against the fp64 oracle on the same (fp32-rounded) cost
 # ---------------------------------------------------------------------------------------------
