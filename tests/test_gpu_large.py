@@ -99,6 +99,8 @@ def test_cost_large(gu, Bx, By, T, D, same):
     (256, 4, 16, 16, 2, "uniform"),
     (200, 5, 12, 12, 1, "video"),      # B and K off the tile sizes (K = 720)
     (1024, 4, 16, 16, 1, "uniform"),
+    (256, 20, 4, 4, 2, "uniform"),     # T * J = 160: config 5's column count in the tiled martingale adjoint (5 groups)
+    (256, 30, 4, 4, 1, "video"),       # T * J = 240: all 8 column groups
 ])
 def test_mixed_loss_large(gu, B, T, H, W, C, kind):
     from oracle import closed_form as cf
