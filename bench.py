@@ -857,6 +857,7 @@ def main():
     hbm_peak = float(pk.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in pk else "fallback 6.65 TB/s"
     stages = stage_times(lib, F, torch, sets_keep, B, K, T, dev)
+    sk_nits = stages.pop("_sinkhorn_nits", None)
     # algorithmic bytes: forward distances read X,Y once (8BK); adjoint reads X,Y and writes g_fake (12BK)
     alg = {"sqdist_tc_kernel": 8.0 * B * K, "grad_tc_kernel": 12.0 * B * K}
     traffic = {}
@@ -883,6 +884,24 @@ def main():
                                "frac_of_hbm_roofline": (20.0 * B * K + 40.0 * B * T * 8) / (ms * 1e-3 / args.steps) / 1e9
                                / hbm_peak}}
 
+    if sk_nits:
+        # The Sinkhorn pair is not a bandwidth kernel: one CTA per problem, every iteration a dependent chain of two
+        # mat-vecs through shared memory.  Its roofline is the bare mat-vec loop of scripts/matvec_probe.py
+        # (kccot_debug_matvec_probe, development build): 478 cycles per iteration on two lanes per row (forward), 569 on
+        # four (backward).  Cycles here = whole launch (prologue and epilogue included) / iterations of the longest solve.
+        mhz = float((clocks or {}).get("sm_mhz") or pk.get("sm_max_mhz") or 1965.0)
+        nmax = max(1, max(sk_nits))
+        fwd_c = stages["sinkhorn_fwd_small_kernel"] * mhz / nmax
+        bwd_c = stages["sinkhorn_bwd_small_kernel"] * mhz / nmax
+        roofline["sinkhorn"] = {"bound": "on-chip latency (3 CTAs on 3 of 148 SMs)", "iterations": sk_nits,
+                                "fwd_cycles_per_counted_iteration": fwd_c, "bwd_cycles_per_step": bwd_c,
+                                "floor_cycles": {"fwd (two lanes per row)": 478, "bwd (four lanes per row)": 569},
+                                "frac_bwd": 569.0 / bwd_c,
+                                "fwd_note": "the forward stops at its bit-exact fixed point (55-71 executed iterations on "
+                                            "these inputs) and fills the history up to the counted 100, so its cycles "
+                                            "per COUNTED iteration can undercut the floor of an executed one; the "
+                                            "backward executes every counted step",
+                                "floor_source": "bare mat-vec pair loop, scripts/matvec_probe.py (round 1, DESIGN.md §5)"}
     cpu = None
     if not args.no_cpu_baseline:
         cpu = cpu_reference_timing(cfg, args.kind, steps=3, warmup=1, budget_s=args.cpu_budget_s)
@@ -968,6 +987,8 @@ def stage_times(lib, F, torch, sets, B, K, T, dev, reps=40):
         b.record()
         torch.cuda.synchronize()
         out[name] = a.elapsed_time(b) / reps * 1e3
+        if name == "sinkhorn_fwd_small_kernel":
+            out["_sinkhorn_nits"] = [int(v) for v in nits.tolist()]      # iterations of the solve that was just timed
     # "grad_tc_kernel" is the whole call: build_w_image_kernel (64 blocks, ~2 us) + the gradient GEMM; the ncu launch
     # list separates them
     return out
