@@ -29,7 +29,8 @@
 extern "C" {
 #endif
 
-#define KCCOT_VERSION 201
+#define KCCOT_VERSION 202
+#define KCCOT_SHARD_FLAGS_PER_RANK 256
 
 /* error codes */
 #define KCCOT_OK 0
@@ -151,7 +152,8 @@ int kccot_shard_bwd_rows(const float* Crows, int Brows, int B, float eps, const 
  * partial[n,0]), all-to-all of the Cbar_xy / Cbar_yy row panels into column panels XYcol, YYcol [B,Brows],
  * SUM of the two M-gradient partials.
  *   mbox_ptrs[r] / flag_ptrs[r]: device pointers (valid on THIS device) to rank r's mailbox
- *   (kccot_shard_mailbox_bytes) and flag array (nranks x uint64, zeroed once).  epoch_base: any number larger
+ *   (kccot_shard_mailbox_bytes) and flag array (nranks x KCCOT_SHARD_FLAGS_PER_RANK x uint64, zeroed once: one flag
+ *   per source rank and CTA of the persistent kernel).  epoch_base: any number larger
  *   than every epoch used so far, identical on all ranks (e.g. launch counter << 24).
  * ------------------------------------------------------------------------------------------ */
 size_t kccot_shard_cost_workspace_bytes(int B, long long K, int Brows);

@@ -10,6 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("KCCOT_LIB", os.path.join(_HERE, "libkccot.so"))
 
 PATH_AUTO, PATH_SIMT, PATH_TCGEN05, FLAG_ACCUMULATE = 0, 1, 2, 16
+SHARD_FLAGS_PER_RANK = 256          # KCCOT_SHARD_FLAGS_PER_RANK of include/kccot.h
 EINVAL, ECUDA, EWORKSPACE, EUNSUPPORTED = -1, -2, -3, -4
 
 _c = ctypes
@@ -84,8 +85,8 @@ def load():
             fn = getattr(lib, name)          # AttributeError if the .so does not export a declared symbol
             fn.restype = res
             fn.argtypes = args
-        if lib.kccot_version() != 201:
-            raise OSError(f"{LIB_PATH}: ABI version {lib.kccot_version()} != 201; rebuild")
+        if lib.kccot_version() != 202:
+            raise OSError(f"{LIB_PATH}: ABI version {lib.kccot_version()} != 202; rebuild")
         _lib = lib
     return _lib
 

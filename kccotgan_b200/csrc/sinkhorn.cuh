@@ -47,7 +47,7 @@ constexpr int kMaxShardRanks = 8;
 struct ShardComm {
   int nranks, rank;
   float* mbox[kMaxShardRanks];                 // mailbox of every rank (device pointers valid on THIS device)
-  unsigned long long* flags[kMaxShardRanks];   // epoch flags of every rank, [nranks] each, zero before first use
+  unsigned long long* flags[kMaxShardRanks];   // epoch flags of every rank, [nranks][KCCOT_SHARD_FLAGS_PER_RANK] each, zero before first use
   unsigned long long epoch0;                   // fresh for every launch and larger than any epoch used before
 };
 bool persist_supported(int Brows, int B, int L);

@@ -124,7 +124,7 @@ __device__ __forceinline__ Geo make_geo(int np, int Brows, int B) {
 struct Xchg {
   int nranks, rank;
   float* mbox[kMaxShardRanks];              // every rank's mailbox [2][np][nranks][2][nv4 * 4] (peer-mapped)
-  unsigned long long* flags[kMaxShardRanks];   // every rank's epoch flags [nranks]; epochs grow monotonically over
+  unsigned long long* flags[kMaxShardRanks];   // every rank's epoch flags [nranks][kFlagStride]; epochs grow monotonically over
   unsigned long long epoch0;                   // launches (the caller passes a fresh base per launch), never reset
 };
 
@@ -139,22 +139,27 @@ __device__ __forceinline__ void xchg_push(const Xchg& X, unsigned long long epoc
     *dst = v;
   }
 }
-// between phase A and B: two grid barriers around the flag handshake of CTA 0
-__device__ __forceinline__ void xchg_sync(cg::grid_group& grid, const Xchg& X, unsigned long long epoch, PState* st) {
-  __threadfence_system();
-  grid.sync();
-  if (blockIdx.x == 0 && threadIdx.x < X.nranks && (int)threadIdx.x != X.rank) {
+// between phase A and B: a handshake PER CTA.  Every rank runs the same grid with the same column slices, CTA c pushes
+// slice c to every peer and afterwards reads only slice c of what the peers pushed, so CTA c needs nothing but "CTA c
+// of every peer has pushed": it publishes flag (rank, c) on every peer and spins on its own flags (r, c).  (The first
+// version funnelled the handshake through CTA 0 between two grid barriers: four grid barriers per iteration instead
+// of the two a single rank needs.)
+constexpr int kFlagStride = KCCOT_SHARD_FLAGS_PER_RANK;     // flags per source rank >= CTAs of the cooperative grid
+__device__ __forceinline__ void xchg_sync(const Xchg& X, unsigned long long epoch, PState* st) {
+  __threadfence_system();                  // this thread's pushes are visible system-wide ...
+  __syncthreads();                         // ... and so are those of the whole CTA, before the flag goes out
+  if ((int)threadIdx.x < X.nranks && (int)threadIdx.x != X.rank) {
     const int r = threadIdx.x;
-    st_release_sys(X.flags[r] + X.rank, epoch);
+    st_release_sys(X.flags[r] + (size_t)X.rank * kFlagStride + blockIdx.x, epoch);
     const unsigned long long t0 = globaltimer_ns();
-    while (ld_acquire_sys(X.flags[X.rank] + r) < epoch) {
+    while (ld_acquire_sys(X.flags[X.rank] + (size_t)r * kFlagStride + blockIdx.x) < epoch) {
       if (globaltimer_ns() - t0 > 4000000000ull) {       // 4 s: a peer died; give up instead of hanging the GPU
         st->error = 1;
         break;
       }
     }
   }
-  grid.sync();
+  __syncthreads();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -457,7 +462,7 @@ __global__ void __launch_bounds__(kNT, 1) sk_persist_fwd_kernel(const __grid_con
       }
     }
     if (multi) {
-      xchg_sync(grid, P.X, epoch, st);
+      xchg_sync(P.X, epoch, st);
       if (!done) {
         const float* mb = P.X.mbox[P.X.rank];
         for (int gi = G.g_begin + tid; gi < G.g_end; gi += kNT) {
@@ -658,7 +663,7 @@ __global__ void __launch_bounds__(kNT, 1) sk_persist_bwd_kernel(const __grid_con
     ++epoch;
     const bool owner = (G.g_end == G.nv4) && (G.g_begin < G.g_end) && tid == 0;
     if (owner) xchg_push(P.X, epoch, P.np, p, G.nv4, G.nv4 - 1, 0, make_float4((float)ld_volatile_i(&st->trip), 0.f, 0.f, 0.f));
-    xchg_sync(grid, P.X, epoch, st);
+    xchg_sync(P.X, epoch, st);
     if (owner) {
       float tsum = 0.f;
       for (int r = 0; r < P.X.nranks; ++r)
@@ -705,7 +710,7 @@ __global__ void __launch_bounds__(kNT, 1) sk_persist_bwd_kernel(const __grid_con
       else fin(gi, A);
     }
     if (multi) {
-      xchg_sync(grid, P.X, epoch, st);
+      xchg_sync(P.X, epoch, st);
       const float* mb = P.X.mbox[P.X.rank];
       for (int gi = G.g_begin + tid; gi < min(G.g_end, B / 4); gi += kNT) {
         float4 A = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -1054,7 +1059,7 @@ int persist_sinkhorn_fwd(const float* C, int np, int Brows, int B, int row0, flo
     P.X.nranks = comm->nranks; P.X.rank = comm->rank; P.X.epoch0 = comm->epoch0;
     for (int r = 0; r < comm->nranks; ++r) { P.X.mbox[r] = comm->mbox[r]; P.X.flags[r] = comm->flags[r]; }
   }
-  const int grid = min(num_sms(), np * Brows);
+  const int grid = min(min(num_sms(), kFlagStride), np * Brows);     // (one exchange flag per CTA: <= kFlagStride)
   const size_t res = resident_smem(np, Brows, B, grid);
   P.resident = res ? 1 : 0;
   const size_t smem = kRedFloats * 4 + res;
@@ -1105,7 +1110,7 @@ int persist_sinkhorn_bwd(const float* C, int np, int Brows, int B, int row0, flo
     P.X.nranks = comm->nranks; P.X.rank = comm->rank; P.X.epoch0 = comm->epoch0;
     for (int r = 0; r < comm->nranks; ++r) { P.X.mbox[r] = comm->mbox[r]; P.X.flags[r] = comm->flags[r]; }
   }
-  const int grid = min(num_sms(), np * Brows);
+  const int grid = min(min(num_sms(), kFlagStride), np * Brows);     // (one exchange flag per CTA: <= kFlagStride)
   const size_t res = resident_smem(np, Brows, B, grid);
   P.resident = res ? 1 : 0;
   const size_t smem = kRedFloats * 4 + res;

@@ -175,7 +175,7 @@ class PeerMailbox:
         self.world = world
         nfl = int(lib.kccot_shard_mailbox_bytes(np_, world, B)) // 4
         self.mbox = symm.empty(nfl, dtype=torch.float32, device=dev)
-        self.flags = symm.empty(max(world, 2), dtype=torch.int64, device=dev)
+        self.flags = symm.empty(max(world, 2) * _lib.SHARD_FLAGS_PER_RANK, dtype=torch.int64, device=dev)
         self.mbox.zero_()
         self.flags.zero_()
         torch.cuda.synchronize(dev)
