@@ -39,17 +39,22 @@ class StubGenerator(nn.Module):
 
 class StubDiscriminator(nn.Module):
     """video [B,H,T,W,C] -> [B,T,J] in (0,1): frame-wise linear features followed by a causal running mean
-    (stands in for the LSTM stack of gan.py:411-429: output t depends on frames <= t only)."""
+    (stands in for the LSTM stack of gan.py:411-429: output t depends on frames <= t only).
+
+    The spatial pooling is a mean over a strided VIEW of the video as it lies in memory ([B,H/p,p,T,W/p,p,C]): no
+    transposed copy of the 31 MB tensor and a broadcast for a backward (a permute + AvgPool2d version spent 0.9 ms of
+    a 2.1 ms training iteration in the permute copies and avg_pool2d_backward)."""
 
     def __init__(self, height, width, channels, J=8, pool=8):
         super().__init__()
-        self.pool = nn.AvgPool2d(pool)
+        self.p = pool
         self.lin = nn.Linear((height // pool) * (width // pool) * channels, J)
 
     def forward(self, video):
         B, H, T, W, C = video.shape
-        frames = video.permute(0, 2, 4, 1, 3).reshape(B * T, C, H, W)
-        feat = self.lin(self.pool(frames).reshape(B * T, -1)).reshape(B, T, -1)
+        p = self.p
+        pooled = video.reshape(B, H // p, p, T, W // p, p, C).mean(dim=(2, 5))          # [B,H/p,T,W/p,C]
+        feat = self.lin(pooled.permute(0, 2, 1, 3, 4).reshape(B * T, -1)).reshape(B, T, -1)
         steps = torch.arange(1, T + 1, device=video.device, dtype=video.dtype).reshape(1, T, 1)
         return torch.sigmoid(torch.cumsum(feat, dim=1) / steps)
 
