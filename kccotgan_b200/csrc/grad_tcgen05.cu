@@ -25,10 +25,11 @@
 //               HBM latency (the first version used two 64 KB stages and starved 44 % of the time).
 //   3xTF32 in ONE instruction per k-step (M = 128, N = 64, K = 8).  The elected lane needs ~30-40 cycles per
 //               tcgen05.mma (descriptor moves to uniform registers; measured with the clock64 timeline) and the
-//               steady state is shared-memory bandwidth (TMA write, converter read / write, operand reads, output
-//               staging): the earlier two-instruction form (N = 64 for W'hi, N = 32 for W'lo, converter rewriting
-//               the hi box rounded) moved 136 KB per 24 KB tile, this one 96 KB.  fp32 accumulate in TMEM, 6
-//               accumulator buffers of 64 columns.
+//               earlier two-instruction form (N = 64 for W'hi, N = 32 for W'lo, converter rewriting the hi box
+//               rounded) was shared-memory bound: 136 KB through the port per 24 KB tile (TMA write, converter read /
+//               write, operand reads, output staging), 1 420 cycles per tile.  This one moves 96 KB and its steady
+//               state is the HBM itself: ~1 100 cycles per tile = 22 B/clk per SM = the measured copy peak.  fp32
+//               accumulate in TMEM, 6 accumulator buffers of 64 columns.
 //   Epilogue:   each of the four epilogue warps owns one quadrant: lanes 0-15 add their two column halves, lanes
 //               16-31 hand W'lo.Zhi down by shuffle; 16 rows per warp are staged in 128-byte-swizzled shared memory
 //               and one TMA store (or reduce-add) writes the [N x 32] box as full 128-byte row segments.
