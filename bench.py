@@ -300,7 +300,7 @@ def run_replica_config(cx, name, kind, steps, smooth):
     cfg, K, config = workload_config(name, kind)
     B, T = cfg["B"], cfg["T"]
     in_bytes = 2 * B * K * 4
-    nsets = max(3, int(300e6 // in_bytes) + 1)
+    nsets = max(NLANES, int(300e6 // in_bytes) + 1)
     ks = KernelSmoothing(temporal_kernel_size=6, spatial_kernel_size=6)       # kernel_train.py:216
     steps_fns = []
     for i in range(nsets):
