@@ -35,6 +35,20 @@ def test_version_and_no_cpu_fallback(lib):
         assert "no CUDA device" in _lib.last_error()
 
 
+def test_header_constants_match_the_python_table():
+    """KCCOT_VERSION and KCCOT_SHARD_FLAGS_PER_RANK of include/kccot.h against kccotgan_b200/_lib.py."""
+    import os
+    import re
+    from kccotgan_b200 import _lib
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "kccot.h")).read()
+    assert int(re.search(r"#define\s+KCCOT_SHARD_FLAGS_PER_RANK\s+(\d+)", hdr).group(1)) == _lib.SHARD_FLAGS_PER_RANK
+    assert int(re.search(r"#define\s+KCCOT_VERSION\s+(\d+)", hdr).group(1)) == _lib.load().kccot_version()
+    # the shared-context entry points reject a hint whose length is not below its period (no CUDA call involved)
+    rc = _lib.load().kccot_mixed_loss_fwd_ctx(None, None, 1, 8, 64, None, None, None, None, 2, 1, 1.0, 1.0, 1, None, None, None,
+                                              None, 0, 0, None, 32, 32)
+    assert rc == _lib.EINVAL and "shared-context" in _lib.last_error()
+
+
 def test_workspace_queries(lib):
     assert lib.kccot_mixed_cost_workspace_bytes(1, 64, 122880) > 0
     assert lib.kccot_cost_workspace_bytes(1, 64, 64, 1000) > 0
