@@ -351,7 +351,7 @@ int launch_cost_finalize(const CostBlocks& blocks, int nblocks, int nprob, int T
     const CostBlock& b = blocks.b[i];
     if (!b.tiled || b.Bx % FT || b.By % FT || b.row_off % FT || b.col_off % FT) all_tiled = false;
   }
-  bool small_ok = all_tiled && nks <= 4 && nprob >= 16 && (T - 1) * J <= 512;
+  bool small_ok = all_tiled && nks <= 4 && nprob >= 16 && (T - 1) * J <= 384;      // (staged rows: <= 199 KB of shared memory)
   for (int i = 0; i < nblocks; ++i)
     if (blocks.b[i].Bx > kFinSmallMaxB || blocks.b[i].By > kFinSmallMaxB) small_ok = false;
   if (small_ok) {
