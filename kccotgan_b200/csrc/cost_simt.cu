@@ -281,16 +281,32 @@ __global__ void __launch_bounds__(256) cost_finalize_small_kernel(CostBlocks blo
   // ---- distance partials: (P_ij + P'_ji) / 2 summed over the k-slabs in fp64 ----
   if (i < b.Bx) {
     const float* pb = b.part + (long long)p * 256 * b.nks * 64;
+    // four outputs at a time: all their loads (2 x nks <= 8 each) go out before the first fp64 add
+    constexpr int MB = 4;
 #pragma unroll
-    for (int m = 0; m < kFinSmallMaxB / 4; ++m) {
-      const int j = l4 + 4 * m;
-      if (j >= b.By || (b.zero_diag && i == j)) continue;
-      const int gi = b.row_off + i, gj = b.col_off + j;
-      const float* pd = pb + ((long long)((gi >> 3) * 16 + (gj >> 3)) * b.nks) * 64 + (gi & 7) * 8 + (gj & 7);
-      const float* pm = pb + ((long long)((gj >> 3) * 16 + (gi >> 3)) * b.nks) * 64 + (gj & 7) * 8 + (gi & 7);
-      double d = 0.0;
-      for (int ks = 0; ks < b.nks; ++ks) d += (double)pd[ks * 64] + (double)pm[ks * 64];
-      acc[m] = 0.5 * d;
+    for (int m0 = 0; m0 < kFinSmallMaxB / 4; m0 += MB) {
+      float vd[MB][4], vm[MB][4];
+#pragma unroll
+      for (int q = 0; q < MB; ++q) {
+        const int j = l4 + 4 * (m0 + q);
+        const bool ok = j < b.By && !(b.zero_diag && i == j);
+        const int gi = b.row_off + i, gj = b.col_off + (ok ? j : 0);
+        const float* pd = pb + ((long long)((gi >> 3) * 16 + (gj >> 3)) * b.nks) * 64 + (gi & 7) * 8 + (gj & 7);
+        const float* pm = pb + ((long long)((gj >> 3) * 16 + (gi >> 3)) * b.nks) * 64 + (gj & 7) * 8 + (gi & 7);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          const bool lk = ok && ks < b.nks;
+          vd[q][ks] = lk ? pd[ks * 64] : 0.f;
+          vm[q][ks] = lk ? pm[ks * 64] : 0.f;
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < MB; ++q) {
+        double d = 0.0;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) d += (double)vd[q][ks] + (double)vm[q][ks];
+        acc[m0 + q] = 0.5 * d;
+      }
     }
   }
   // ---- martingale terms: thread (i, l4) owns row i and the columns l4, l4 + 4, ...; one 16-byte load of its h row
@@ -300,14 +316,37 @@ __global__ void __launch_bounds__(256) cost_finalize_small_kernel(CostBlocks blo
     const float* M = pr ? b.M2 : b.M1;
     if (h == nullptr) continue;
     __syncthreads();
-    for (int e = tid; e < b.Bx * tj4; e += 256) {
-      const int r = e / tj4, c = e - r * tj4;
-      hs[r * ldh + c] = (c < tj1) ? h[((long long)p * b.Bx + r) * TJ + c] : 0.f;
+    // staging with six loads in flight per thread (one load -> one store per iteration made the kernel a chain of
+    // 36 memory latencies: 120 us for 256 problems)
+    constexpr int SU = 6;
+    for (int e0 = tid; e0 < b.Bx * tj4; e0 += 256 * SU) {
+      float v[SU];
+#pragma unroll
+      for (int u = 0; u < SU; ++u) {
+        const int e = e0 + 256 * u, r = e / tj4, c = e - r * tj4;
+        v[u] = (e < b.Bx * tj4 && c < tj1) ? h[((long long)p * b.Bx + r) * TJ + c] : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < SU; ++u) {
+        const int e = e0 + 256 * u, r = e / tj4, c = e - r * tj4;
+        if (e < b.Bx * tj4) hs[r * ldh + c] = v[u];
+      }
     }
-    for (int e = tid; e < b.By * tj4; e += 256) {
-      const int r = e / tj4, c = e - r * tj4;
-      const float* Mr = M + ((long long)p * b.By + r) * TJ + c;
-      dms[r * ldh + c] = (c < tj1) ? Mr[J] - Mr[0] : 0.f;
+    for (int e0 = tid; e0 < b.By * tj4; e0 += 256 * SU) {
+      float v0[SU], v1[SU];
+#pragma unroll
+      for (int u = 0; u < SU; ++u) {
+        const int e = e0 + 256 * u, r = e / tj4, c = e - r * tj4;
+        const bool ok = e < b.By * tj4 && c < tj1;
+        const float* Mr = M + ((long long)p * b.By + (ok ? r : 0)) * TJ + (ok ? c : 0);
+        v0[u] = ok ? Mr[0] : 0.f;
+        v1[u] = ok ? Mr[J] : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < SU; ++u) {
+        const int e = e0 + 256 * u, r = e / tj4, c = e - r * tj4;
+        if (e < b.By * tj4) dms[r * ldh + c] = v1[u] - v0[u];
+      }
     }
     __syncthreads();
     if (i < b.Bx) {
